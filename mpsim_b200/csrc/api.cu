@@ -1,0 +1,299 @@
+// extern "C" surface of libmpsim_b200 (see include/mpsim_b200.h for the contract).
+#include "common.cuh"
+#include <string.h>
+#include <string>
+
+int launch_gate1(const mpsb_gate1_desc* descs, int ndesc, int nbatch, int d, int max_site_elems, cudaStream_t st);
+int launch_scale(const mpsb_site_ref* sites, int nsites, int nbatch, int d, const float* factors,
+                 int max_site_elems, cudaStream_t st);
+int launch_amplitudes(const mpsb_site_ref* sites, int nsites, int nbatch, int d, int max_chi,
+                      const uint8_t* bits, int nbits, cf* out, cudaStream_t st);
+
+static thread_local char g_err[512] = "";
+
+void mpsb_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+namespace {
+
+__global__ void set_ones_kernel(cf* E, int64_t stride, int nbatch) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nbatch) E[(int64_t)b * stride] = cf_make(1.f, 0.f);
+}
+
+__global__ void gather_first_kernel(const cf* E, int64_t stride, int nbatch, cf* out) {
+    int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < nbatch) out[b] = E[(int64_t)b * stride];
+}
+
+// out[job][c][r] = in[job][r][c]   (in: rows x cols)
+__global__ void transpose_kernel(const cf* __restrict__ in, cf* __restrict__ out, int rows, int cols) {
+    __shared__ cf tile[32][33];
+    const cf* src = in + (int64_t)blockIdx.z * rows * cols;
+    cf* dst = out + (int64_t)blockIdx.z * rows * cols;
+    int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int r = r0 + i, c = c0 + threadIdx.x;
+        if (r < rows && c < cols) tile[i][threadIdx.x] = src[(int64_t)r * cols + c];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        int c = c0 + i, r = r0 + threadIdx.x;
+        if (r < rows && c < cols) dst[(int64_t)c * rows + r] = tile[threadIdx.x][i];
+    }
+}
+
+struct Gate2Plan {
+    int m, n, nv, L;
+    bool small;
+    size_t x_elems, extra_elems, job_elems;
+};
+
+Gate2Plan plan_gate2(int d, int chiL, int chiR, int lc) {
+    Gate2Plan p;
+    p.m = d * chiL; p.n = d * chiR;
+    p.nv = lc ? p.m : p.n;
+    p.L = lc ? p.n : p.m;
+    p.small = p.m <= MPSB_MAX_SMALL_DIM && p.n <= MPSB_MAX_SMALL_DIM;
+    p.x_elems = (size_t)p.m * p.n;
+    p.extra_elems = p.small ? svd_small_global_z_elems(p.nv, p.L) : svd_large_workspace_elems(p.nv, p.L);
+    p.job_elems = align_up(p.x_elems, 16) + align_up(p.extra_elems, 16);
+    return p;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mpsb_version(void) { return MPSB_VERSION; }
+const char* mpsb_last_error(void) { return g_err; }
+
+int mpsb_device_info(int* sm_count, int* max_smem_optin, int* cc_major, int* cc_minor) {
+    int dev = 0;
+    MPSB_CUDA(cudaGetDevice(&dev));
+    if (sm_count) MPSB_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+    if (max_smem_optin) MPSB_CUDA(cudaDeviceGetAttribute(max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    if (cc_major) MPSB_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (cc_minor) MPSB_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    return 0;
+}
+
+size_t mpsb_gate2_workspace_bytes(int ndesc, int nbatch, int d, int chiL, int chiM, int chiR, int k) {
+    (void)chiM; (void)k;
+    if (ndesc <= 0 || nbatch <= 0 || chiL <= 0 || chiR <= 0) return 0;
+    // worst of the two orientations so one workspace serves both canonical forms
+    size_t a = plan_gate2(d, chiL, chiR, 1).job_elems, b = plan_gate2(d, chiL, chiR, 0).job_elems;
+    return (a > b ? a : b) * sizeof(cf) * (size_t)ndesc * nbatch + 256;
+}
+
+int mpsb_apply_gate2(const mpsb_gate2_desc* descs_dev, int ndesc, int nbatch,
+                     int d, int chiL, int chiM, int chiR, int k, int left_canonical,
+                     void* workspace, size_t workspace_bytes, int32_t* info, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    MPSB_ARG(descs_dev != nullptr, "apply_gate2: descs is NULL");
+    MPSB_ARG(ndesc >= 0 && nbatch >= 0, "apply_gate2: negative counts");
+    MPSB_ARG(d >= 2, "apply_gate2: qudit dimension %d < 2", d);
+    MPSB_ARG(chiL >= 0 && chiM >= 0 && chiR >= 0, "apply_gate2: negative bond dimension");
+    int njobs = ndesc * nbatch;
+    if (njobs == 0 || chiL == 0 || chiR == 0 || k == 0) return 0;   // nothing to write (empty tensors)
+    int mn = d * (chiL < chiR ? chiL : chiR);
+    MPSB_ARG(k > 0 && k <= mn, "apply_gate2: k=%d outside [0, %d]", k, mn);
+    MPSB_ARG(njobs <= 65535, "apply_gate2: %d applications in one call (max 65535); split the call", njobs);
+    Gate2Plan p = plan_gate2(d, chiL, chiR, left_canonical ? 1 : 0);
+    size_t need = p.job_elems * sizeof(cf) * (size_t)njobs;
+    MPSB_ARG(workspace != nullptr && workspace_bytes >= need, "apply_gate2: workspace %zu B < %zu B", workspace_bytes, need);
+    MPSB_ARG(((uintptr_t)workspace & 15) == 0, "apply_gate2: workspace must be 16-byte aligned");
+    cf* ws = (cf*)workspace;
+    cf* X = ws;                                              // [njobs][x_elems]
+    cf* extra = ws + align_up(p.x_elems, 16) * (size_t)njobs;     // [njobs][extra]
+    int rc = launch_theta(descs_dev, ndesc, nbatch, d, chiL, chiM, chiR, left_canonical ? 0 : 1,
+                          X, (int64_t)align_up(p.x_elems, 16), st);
+    if (rc) return rc;
+    if (p.small) {
+        return launch_svd_small(X, (int64_t)align_up(p.x_elems, 16), njobs, p.nv, p.L, k, left_canonical ? 1 : 0,
+                                descs_dev, ndesc, nbatch, nullptr, 0, nullptr, 0, nullptr, 0, info,
+                                p.extra_elems ? extra : nullptr, st);
+    }
+    return launch_svd_large(X, (int64_t)align_up(p.x_elems, 16), njobs, p.nv, p.L, k, left_canonical ? 1 : 0,
+                            descs_dev, ndesc, nbatch, nullptr, 0, nullptr, 0, nullptr, 0, info, extra, st);
+}
+
+int mpsb_apply_gate1(const mpsb_gate1_desc* descs_dev, int ndesc, int nbatch, int d,
+                     int max_site_elems, void* stream) {
+    MPSB_ARG(descs_dev != nullptr || ndesc == 0, "apply_gate1: descs is NULL");
+    return launch_gate1(descs_dev, ndesc, nbatch, d, max_site_elems, (cudaStream_t)stream);
+}
+
+size_t mpsb_inner_workspace_bytes(int nbatch, int d, int max_chi_a, int max_chi_b) {
+    if (max_chi_a < 1) max_chi_a = 1;
+    if (max_chi_b < 1) max_chi_b = 1;
+    size_t e = align_up((size_t)max_chi_a * max_chi_b, 16);
+    size_t t = align_up((size_t)max_chi_b * d * max_chi_a, 16);
+    return (2 * e + t) * sizeof(cf) * (size_t)nbatch + 256;
+}
+
+int mpsb_inner_products(const mpsb_site_ref* a, const mpsb_site_ref* b, int nsites,
+                        int nbatch, int d, void* out, void* workspace, size_t workspace_bytes,
+                        void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    MPSB_ARG(a && b && nsites >= 1 && nbatch >= 1, "inner_products: bad arguments");
+    int ma = 1, mb = 1;
+    for (int s = 0; s < nsites; ++s) {
+        MPSB_ARG(a[s].chiL >= 0 && a[s].chiR >= 0 && b[s].chiL >= 0 && b[s].chiR >= 0, "inner_products: negative bond");
+        if (s > 0) MPSB_ARG(a[s].chiL == a[s - 1].chiR && b[s].chiL == b[s - 1].chiR, "inner_products: bond mismatch at site %d", s);
+        ma = a[s].chiL > ma ? a[s].chiL : ma; ma = a[s].chiR > ma ? a[s].chiR : ma;
+        mb = b[s].chiL > mb ? b[s].chiL : mb; mb = b[s].chiR > mb ? b[s].chiR : mb;
+    }
+    MPSB_ARG(a[0].chiL == 1 && b[0].chiL == 1 && a[nsites - 1].chiR == 1 && b[nsites - 1].chiR == 1,
+             "inner_products: chain ends must have bond dimension 1");
+    MPSB_ARG(workspace_bytes >= mpsb_inner_workspace_bytes(nbatch, d, ma, mb), "inner_products: workspace too small");
+    size_t es = align_up((size_t)ma * mb, 16), ts = align_up((size_t)mb * d * ma, 16);
+    cf* E0 = (cf*)workspace;
+    cf* E1 = E0 + es * nbatch;
+    cf* T = E1 + es * nbatch;
+    MPSB_CUDA(cudaMemsetAsync(E0, 0, es * nbatch * sizeof(cf), st));
+    set_ones_kernel<<<(nbatch + 127) / 128, 128, 0, st>>>(E0, (int64_t)es, nbatch);
+    MPSB_LAUNCH_CHECK("set_ones_kernel");
+    cf* Ec = E0; cf* En = E1;
+    for (int s = 0; s < nsites; ++s) {
+        int xa = a[s].chiL, xa2 = a[s].chiR, yb = b[s].chiL, yb2 = b[s].chiR;
+        // T[y][(p,x')] = sum_x E[x][y] A[x][(p,x')]
+        int rc = launch_cgemm(Ec, 1, yb, 0, (int64_t)es,
+                              (const cf*)a[s].site, (int64_t)d * xa2, 1, 0, a[s].bs,
+                              T, (int64_t)d * xa2, (int64_t)ts, yb, d * xa2, xa, nbatch, st);
+        if (rc) return rc;
+        // E'[x'][y'] = sum_{(y,p)} T[(y,p)][x'] conj(B[(y,p)][y'])
+        rc = launch_cgemm(T, 1, xa2, 0, (int64_t)ts,
+                          (const cf*)b[s].site, yb2, 1, 1, b[s].bs,
+                          En, yb2, (int64_t)es, xa2, yb2, yb * d, nbatch, st);
+        if (rc) return rc;
+        cf* t = Ec; Ec = En; En = t;
+    }
+    gather_first_kernel<<<(nbatch + 127) / 128, 128, 0, st>>>(Ec, (int64_t)es, nbatch, (cf*)out);
+    MPSB_LAUNCH_CHECK("gather_first_kernel");
+    return 0;
+}
+
+int mpsb_scale_sites(const mpsb_site_ref* sites_dev, int nsites, int nbatch, int d,
+                     const float* factors_dev, int max_site_elems, void* stream) {
+    MPSB_ARG(sites_dev && factors_dev, "scale_sites: NULL argument");
+    return launch_scale(sites_dev, nsites, nbatch, d, factors_dev, max_site_elems, (cudaStream_t)stream);
+}
+
+size_t mpsb_wavefunction_workspace_bytes(const mpsb_site_ref* s, int nsites, int d) {
+    size_t rows = 1, mx = 1;
+    for (int i = 0; i < nsites; ++i) {
+        rows *= (size_t)d;
+        size_t e = rows * (size_t)(s[i].chiR > 0 ? s[i].chiR : 1);
+        if (e > mx) mx = e;
+    }
+    return 2 * align_up(mx, 16) * sizeof(cf) + 256;
+}
+
+int mpsb_wavefunction(const mpsb_site_ref* s, int nsites, int d, int batch_index,
+                      void* out, void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    MPSB_ARG(s && nsites >= 2 && out, "wavefunction: bad arguments");
+    MPSB_ARG(s[0].chiL == 1 && s[nsites - 1].chiR == 1, "wavefunction: chain ends must have bond dimension 1");
+    MPSB_ARG(workspace_bytes >= mpsb_wavefunction_workspace_bytes(s, nsites, d), "wavefunction: workspace too small");
+    size_t total = 1;
+    bool empty = false;
+    for (int i = 0; i < nsites; ++i) {
+        total *= (size_t)d;
+        if (i > 0) MPSB_ARG(s[i].chiL == s[i - 1].chiR, "wavefunction: bond mismatch at site %d", i);
+        if (s[i].chiR == 0) empty = true;
+    }
+    if (empty) {     // a bond of dimension 0 (maxsvals=0, core_test.py:1093-1101): psi = 0
+        MPSB_CUDA(cudaMemsetAsync(out, 0, total * sizeof(cf), st));
+        return 0;
+    }
+    size_t half = (workspace_bytes - 256) / 2 / sizeof(cf) / 16 * 16;
+    cf* buf[2] = {(cf*)workspace, (cf*)workspace + half};
+    const cf* cur = (const cf*)s[0].site + (int64_t)batch_index * s[0].bs;    // [d][chi1]
+    size_t rows = d;
+    for (int i = 1; i < nsites; ++i) {
+        cf* dst = (i == nsites - 1) ? (cf*)out : buf[i & 1];
+        int chi = s[i].chiL, chi2 = s[i].chiR;
+        MPSB_ARG(rows <= 0x7fffffff, "wavefunction: too many qudits");
+        int rc = launch_cgemm(cur, chi, 1, 0, 0,
+                              (const cf*)s[i].site + (int64_t)batch_index * s[i].bs, (int64_t)d * chi2, 1, 0, 0,
+                              dst, (int64_t)d * chi2, 0, (int)rows, d * chi2, chi, 1, st);
+        if (rc) return rc;
+        cur = dst;
+        rows *= (size_t)d;
+    }
+    return 0;
+}
+
+int mpsb_amplitudes(const mpsb_site_ref* sites_dev, int nsites, int nbatch, int d, int max_chi,
+                    const uint8_t* bits_dev, int nbits, void* out, void* stream) {
+    MPSB_ARG(sites_dev && bits_dev && out, "amplitudes: NULL argument");
+    return launch_amplitudes(sites_dev, nsites, nbatch, d, max_chi, bits_dev, nbits, (cf*)out, (cudaStream_t)stream);
+}
+
+int mpsb_cgemm(const void* A, int64_t a_rs, int64_t a_cs, int conj_a, int64_t a_bs,
+               const void* B, int64_t b_rs, int64_t b_cs, int conj_b, int64_t b_bs,
+               void* C, int64_t c_ld, int64_t c_bs, int M, int N, int K, int nbatch, void* stream) {
+    return launch_cgemm((const cf*)A, a_rs, a_cs, conj_a, a_bs, (const cf*)B, b_rs, b_cs, conj_b, b_bs,
+                        (cf*)C, c_ld, c_bs, M, N, K, nbatch, (cudaStream_t)stream);
+}
+
+int mpsb_theta(const mpsb_gate2_desc* descs_dev, int ndesc, int nbatch, int d,
+               int chiL, int chiM, int chiR, void* out, void* workspace, size_t workspace_bytes,
+               void* stream) {
+    (void)workspace; (void)workspace_bytes;
+    MPSB_ARG(descs_dev && out, "theta: NULL argument");
+    return launch_theta(descs_dev, ndesc, nbatch, d, chiL, chiM, chiR, 0, (cf*)out,
+                        (int64_t)d * chiL * d * chiR, (cudaStream_t)stream);
+}
+
+size_t mpsb_svd_workspace_bytes(int njobs, int m, int n) {
+    if (njobs <= 0 || m <= 0 || n <= 0) return 0;
+    bool small = m <= MPSB_MAX_SMALL_DIM && n <= MPSB_MAX_SMALL_DIM;
+    size_t ex_a = small ? svd_small_global_z_elems(m, n) : svd_large_workspace_elems(m, n);
+    size_t ex_b = small ? svd_small_global_z_elems(n, m) : svd_large_workspace_elems(n, m);
+    size_t ex = ex_a > ex_b ? ex_a : ex_b;
+    return (align_up((size_t)m * n, 16) + align_up(ex, 16)) * sizeof(cf) * (size_t)njobs + 256;
+}
+
+int mpsb_svd(const void* mats, int njobs, int m, int n, int k, int left_canonical,
+             void* left, void* right, float* svals, int32_t* info,
+             void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    MPSB_ARG(mats && left && right, "svd: NULL argument");
+    MPSB_ARG(m >= 1 && n >= 1, "svd: empty matrix");
+    MPSB_ARG(njobs >= 0 && njobs <= 65535, "svd: njobs %d outside [0, 65535]", njobs);
+    if (njobs == 0 || k == 0) return 0;
+    MPSB_ARG(workspace_bytes >= mpsb_svd_workspace_bytes(njobs, m, n), "svd: workspace too small");
+    int lc = left_canonical ? 1 : 0;
+    int nv = lc ? m : n, L = lc ? n : m;
+    int mn = m < n ? m : n;
+    bool small = m <= MPSB_MAX_SMALL_DIM && n <= MPSB_MAX_SMALL_DIM;
+    size_t xs = align_up((size_t)m * n, 16);
+    cf* X = (cf*)workspace;
+    cf* extra = X + xs * njobs;
+    if (lc) {
+        MPSB_CUDA(cudaMemcpy2DAsync(X, xs * sizeof(cf), mats, (size_t)m * n * sizeof(cf), (size_t)m * n * sizeof(cf),
+                                    njobs, cudaMemcpyDeviceToDevice, st));
+    } else {
+        // X[job] = mats[job]^T, written at the padded job stride
+        for (int j0 = 0; j0 < njobs; ++j0) {
+            dim3 grid((n + 31) / 32, (m + 31) / 32, 1);
+            transpose_kernel<<<grid, dim3(32, 8), 0, st>>>((const cf*)mats + (size_t)j0 * m * n, X + (size_t)j0 * xs, m, n);
+        }
+        MPSB_LAUNCH_CHECK("transpose_kernel");
+    }
+    if (small)
+        return launch_svd_small(X, (int64_t)xs, njobs, nv, L, k, lc, nullptr, 0, 1,
+                                (cf*)left, (int64_t)m * k, (cf*)right, (int64_t)k * n, svals, mn, info,
+                                extra, st);
+    return launch_svd_large(X, (int64_t)xs, njobs, nv, L, k, lc, nullptr, 0, 1,
+                            (cf*)left, (int64_t)m * k, (cf*)right, (int64_t)k * n, svals, mn, info,
+                            extra, st);
+}
+
+}  // extern "C"

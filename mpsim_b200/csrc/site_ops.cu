@@ -1,0 +1,132 @@
+// HBM-bound site kernels: one-qudit gate, per-chain scaling, amplitude chains.
+#include "common.cuh"
+
+namespace {
+
+// A'[l][o][r] = sum_p g[o][p] A[l][p][r]     (mpsim/core.py:819-826)
+// One thread per (l, r): reads the d physical components (each a coalesced stream over r),
+// writes d.  Algorithmic traffic: 16*d*chiL*chiR bytes per site.
+template <int D>
+__global__ void __launch_bounds__(256)
+gate1_kernel(const mpsb_gate1_desc* __restrict__ descs, int nbatch) {
+    const int job = blockIdx.y;
+    const int di = job / nbatch, bi = job % nbatch;
+    const mpsb_gate1_desc d = descs[di];
+    const cf* __restrict__ A = (const cf*)d.site + (int64_t)bi * d.bs_site;
+    cf* __restrict__ O = (cf*)d.out + (int64_t)bi * d.bs_out;
+    const cf* __restrict__ G = (const cf*)d.gate + (int64_t)bi * d.bs_gate;
+    cf g[D][D];
+#pragma unroll
+    for (int o = 0; o < D; ++o)
+#pragma unroll
+        for (int p = 0; p < D; ++p) g[o][p] = G[o * D + p];
+    const int chiR = d.chiR;
+    const int64_t n = (int64_t)d.chiL * chiR;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t l = e / chiR;
+        int r = (int)(e - l * chiR);
+        int64_t base = l * D * chiR + r;
+        cf a[D];
+#pragma unroll
+        for (int p = 0; p < D; ++p) a[p] = A[base + (int64_t)p * chiR];
+#pragma unroll
+        for (int o = 0; o < D; ++o) {
+            cf t = cf_make(0.f, 0.f);
+#pragma unroll
+            for (int p = 0; p < D; ++p) t = cf_fma(g[o][p], a[p], t);
+            O[base + (int64_t)o * chiR] = t;
+        }
+    }
+}
+
+// site <- factor[b] * site     (mpsim/core.py:590-594)
+__global__ void __launch_bounds__(256)
+scale_kernel(const mpsb_site_ref* __restrict__ sites, int nbatch, int d, const float* __restrict__ factors) {
+    const int job = blockIdx.y;
+    const int si = job / nbatch, bi = job % nbatch;
+    const mpsb_site_ref s = sites[si];
+    cf* A = (cf*)s.site + (int64_t)bi * s.bs;
+    const float f = factors[bi];
+    const int64_t n = (int64_t)s.chiL * d * s.chiR;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        cf v = A[e];
+        A[e] = cf_make(f * v.x, f * v.y);
+    }
+}
+
+// <bits|psi> = A_0[:, b0, :] A_1[:, b1, :] ... : one CTA per (bitstring, batch member); the
+// running row vector lives in shared memory, each step is a coalesced vector-matrix product.
+__global__ void __launch_bounds__(256)
+amplitude_kernel(const mpsb_site_ref* __restrict__ sites, int nsites, int nbatch, int d, int max_chi,
+                 const uint8_t* __restrict__ bits, int nbits, cf* __restrict__ out) {
+    extern __shared__ float4 smem_raw[];
+    cf* v0 = (cf*)smem_raw;
+    cf* v1 = v0 + max_chi;
+    const int bit_id = blockIdx.x, bi = blockIdx.y;
+    const uint8_t* mybits = bits + (size_t)bit_id * nsites;
+    for (int i = threadIdx.x; i < max_chi; i += blockDim.x) v0[i] = cf_make(i == 0 ? 1.f : 0.f, 0.f);
+    __syncthreads();
+    cf* cur = v0; cf* nxt = v1;
+    for (int s = 0; s < nsites; ++s) {
+        const mpsb_site_ref sr = sites[s];
+        const cf* A = (const cf*)sr.site + (int64_t)bi * sr.bs;
+        const int b = mybits[s];
+        const int chiL = sr.chiL, chiR = sr.chiR;
+        for (int r = threadIdx.x; r < chiR; r += blockDim.x) {
+            cf acc = cf_make(0.f, 0.f);
+            for (int l = 0; l < chiL; ++l) acc = cf_fma(cur[l], A[((int64_t)l * d + b) * chiR + r], acc);
+            nxt[r] = acc;
+        }
+        __syncthreads();
+        cf* t = cur; cur = nxt; nxt = t;
+    }
+    if (threadIdx.x == 0) out[(size_t)bi * nbits + bit_id] = cur[0];
+}
+
+}  // namespace
+
+int launch_gate1(const mpsb_gate1_desc* descs, int ndesc, int nbatch, int d, int max_site_elems, cudaStream_t st) {
+    int njobs = ndesc * nbatch;
+    if (njobs <= 0) return 0;
+    MPSB_ARG(njobs <= 65535, "gate1: too many jobs in one call (%d > 65535)", njobs);
+    int per = max_site_elems / d;
+    int bx = (per + 255) / 256;
+    if (bx < 1) bx = 1;
+    if (bx > 1184) bx = 1184;      // 8 x 148 SMs; the kernel grid-strides beyond that
+    dim3 grid(bx, njobs);
+    switch (d) {
+        case 2: gate1_kernel<2><<<grid, 256, 0, st>>>(descs, nbatch); break;
+        case 3: gate1_kernel<3><<<grid, 256, 0, st>>>(descs, nbatch); break;
+        case 4: gate1_kernel<4><<<grid, 256, 0, st>>>(descs, nbatch); break;
+        default: MPSB_ARG(false, "gate1: qudit dimension %d not supported on device (2..4)", d);
+    }
+    MPSB_LAUNCH_CHECK("gate1_kernel");
+    return 0;
+}
+
+int launch_scale(const mpsb_site_ref* sites, int nsites, int nbatch, int d, const float* factors,
+                 int max_site_elems, cudaStream_t st) {
+    int njobs = nsites * nbatch;
+    if (njobs <= 0) return 0;
+    MPSB_ARG(njobs <= 65535, "scale: too many jobs in one call (%d > 65535)", njobs);
+    int bx = (max_site_elems + 255) / 256;
+    if (bx < 1) bx = 1;
+    if (bx > 1184) bx = 1184;
+    scale_kernel<<<dim3(bx, njobs), 256, 0, st>>>(sites, nbatch, d, factors);
+    MPSB_LAUNCH_CHECK("scale_kernel");
+    return 0;
+}
+
+int launch_amplitudes(const mpsb_site_ref* sites, int nsites, int nbatch, int d, int max_chi,
+                      const uint8_t* bits, int nbits, cf* out, cudaStream_t st) {
+    if (nbits <= 0 || nbatch <= 0) return 0;
+    MPSB_ARG(nbatch <= 65535, "amplitudes: nbatch %d > 65535", nbatch);
+    if (max_chi < 1) max_chi = 1;
+    size_t smem = (size_t)2 * max_chi * sizeof(cf);
+    MPSB_ARG(smem <= 200 * 1024, "amplitudes: max_chi %d too large", max_chi);
+    if (smem > 48 * 1024)
+        MPSB_CUDA(cudaFuncSetAttribute(amplitude_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    amplitude_kernel<<<dim3(nbits, nbatch), 256, smem, st>>>(sites, nsites, nbatch, d, max_chi, bits, nbits, out);
+    MPSB_LAUNCH_CHECK("amplitude_kernel");
+    return 0;
+}

@@ -1,0 +1,416 @@
+// Truncated SVD for d*chi <= 128: one CTA per matrix, everything resident in shared memory.
+//
+// Replaces tn.split_node_full_svd -> np.linalg.svd (LAPACK zgesdd) + slice [:k] + the two
+// absorb contractions of mpsim/core.py:1132-1152.
+//
+// Input  X [nv][L] : the theta matrix oriented so that its ROWS are the vectors to
+//                    orthogonalise (left-canonical: X = theta, nv = d*chiL, L = d*chiR;
+//                    otherwise X = theta^T).
+// Method (CPU model with identical arithmetic: tests/_jacobi_model.py):
+//   1. Householder QR preconditioning  X = Q R ; Y <- R, Z <- Q^H.  Jacobi on R converges in
+//      ~9 sweeps independently of how graded the spectrum is (plain Jacobi on X needs 15-25).
+//   2. One-sided Jacobi on the rows of Y, the same 2x2 unitaries accumulated into Z, so that
+//      Z X0 == Y always.  Rows are visited by a block tournament: 4-row blocks are paired by the
+//      circle method; a warp owns a pair of blocks, keeps its 8 rows of Y and Z in registers
+//      (lane owns elements lane, lane+32, ...) and performs the 16 cross rotations (plus the 12
+//      intra-block ones in the first round of a sweep) with warp-shuffle reductions.
+//   3. sigma_j = |Y_j|, stable descending rank sort (ties keep the lower index: this is what
+//      reproduces the reference on Bell + maxsvals=1, README.md:48-53), keep the first k.
+//   4. Split/absorb without any division: the isometry is conj(Z) (a product of unitaries, so
+//      orthonormal even for zero singular values, like LAPACK's), the weighted factor is Y:
+//        left-canonical : left  = Z_k^H   (U)     right = Y_k      (S.Vh)
+//        otherwise      : left  = Y_k^T   (U.S)   right = conj(Z_k) (Vh)
+//      left.right == exact rank-k projection of theta whether or not Jacobi converged.
+#include "common.cuh"
+
+namespace {
+
+constexpr int ST = 256;          // threads per CTA
+constexpr int NW = ST / 32;      // warps
+constexpr int EPL = 4;           // elements per lane per row (row length <= 128)
+
+struct SvdSmallParams {
+    const cf* X; int64_t x_stride;
+    int nv, L, k, lc;
+    int nvp, LS, ZS, LC, ZC;     // padded rows, smem strides, columns touched by lanes
+    int nz_smem;                 // Z rows [0, nz_smem) live in shared memory, the rest in zg
+    cf* zg; int64_t zg_stride;
+    const mpsb_gate2_desc* descs; int nbatch;     // output mode A (descs != nullptr)
+    cf* left; int64_t left_stride; cf* right; int64_t right_stride;   // output mode B
+    float* svals; int64_t svals_stride;
+    int32_t* info;
+    int max_sweeps; float tol2;
+};
+
+__device__ __forceinline__ void rot_params(float a, float b, float gr, float gi, float g2,
+                                           float& c, float& sr, float& si, float& tg) {
+    // (c, s) of [[c, s], [-conj(s), c]] diagonalising [[a, g], [conj(g), b]]; s first, then
+    // c = sqrt(1 - |s|^2) derived from s (series near 1) so the rotation is unitary to rounding
+    // WITHOUT bias -- see tests/_jacobi_model.py:rotation_params.
+    float rg = rsqrtf(g2);
+    float zeta = (a - b) * (0.5f * rg);
+    float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
+    float ct = (t * rsqrtf(fmaf(t, t, 1.0f))) * rg;
+    sr = ct * gr;
+    si = ct * gi;
+    float h = fmaf(sr, sr, si * si);
+    float poly = fmaf(h, fmaf(h, fmaf(h, fmaf(h, 0.02734375f, 0.0390625f), 0.0625f), 0.125f), 0.5f);
+    float c_series = fmaf(-h, poly, 1.0f);
+    float c_sqrt = sqrtf(fmaf(-sr, sr, fmaf(-si, si, 1.0f)));
+    c = (h < 0.0625f) ? c_series : c_sqrt;
+    tg = t * (g2 * rg);
+}
+
+__device__ __forceinline__ void rot_apply(float c, float sr, float si, cf& p, cf& q) {
+    cf np_, nq_;
+    np_.x = fmaf(c, p.x, fmaf(sr, q.x, -(si * q.y)));
+    np_.y = fmaf(c, p.y, fmaf(sr, q.y, si * q.x));
+    nq_.x = fmaf(c, q.x, -fmaf(sr, p.x, si * p.y));
+    nq_.y = fmaf(c, q.y, fmaf(si, p.x, -(sr * p.y)));
+    p = np_;
+    q = nq_;
+}
+
+// One sub-round: NP disjoint pairs (PA[i], PB[i]) of the warp's 8 rows.
+template <int NP>
+__device__ __forceinline__ int sub_round(cf (&y)[8][EPL], cf (&z)[8][EPL], float (&a)[8],
+                                         const int (&PA)[NP], const int (&PB)[NP], float tol2) {
+    float gr[NP], gi[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        float r = 0.f, m = 0.f;
+#pragma unroll
+        for (int t = 0; t < EPL; ++t) {
+            cf p = y[PA[i]][t], q = y[PB[i]][t];
+            r = fmaf(p.x, q.x, r); r = fmaf(p.y, q.y, r);
+            m = fmaf(p.y, q.x, m); m = fmaf(-p.x, q.y, m);
+        }
+        gr[i] = r; gi[i] = m;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int i = 0; i < NP; ++i) {
+            gr[i] += __shfl_xor_sync(0xffffffffu, gr[i], o);
+            gi[i] += __shfl_xor_sync(0xffffffffu, gi[i], o);
+        }
+    }
+    int nrot = 0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) {
+        float g2 = fmaf(gr[i], gr[i], gi[i] * gi[i]);
+        float ap = a[PA[i]], aq = a[PB[i]];
+        if (g2 > tol2 * ap * aq && g2 > 1e-30f) {      // warp-uniform (all lanes hold the sums)
+            float c, sr, si, tg;
+            rot_params(ap, aq, gr[i], gi[i], g2, c, sr, si, tg);
+#pragma unroll
+            for (int t = 0; t < EPL; ++t) {
+                rot_apply(c, sr, si, y[PA[i]][t], y[PB[i]][t]);
+                rot_apply(c, sr, si, z[PA[i]][t], z[PB[i]][t]);
+            }
+            a[PA[i]] = fmaxf(ap + tg, 0.f);
+            a[PB[i]] = fmaxf(aq - tg, 0.f);
+            ++nrot;
+        }
+    }
+    return nrot;
+}
+
+__global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
+    extern __shared__ float4 smem_raw[];
+    const int job = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nv = P.nv, L = P.L, nvp = P.nvp, LS = P.LS, ZS = P.ZS;
+
+    cf* Ys = (cf*)smem_raw;                        // [nvp][LS]
+    cf* Zs = Ys + (size_t)nvp * LS;                // [nz_smem][ZS]
+    cf* vbuf = Zs + (size_t)P.nz_smem * ZS;        // [2][nvp]
+    float* sig = (float*)(vbuf + 2 * nvp);         // [nvp]
+    int* perm = (int*)(sig + nvp);                 // [nvp]
+    float* scal = (float*)(perm + nvp);            // [8]
+    int* cnt = (int*)(scal + 8);                   // [2]
+    cf* zg = P.zg + (size_t)job * P.zg_stride;
+    const int nzs = P.nz_smem;
+    auto zrow = [&](int i) -> cf* { return i < nzs ? Zs + (size_t)i * ZS : zg + (size_t)(i - nzs) * ZS; };
+
+    // ---- phase 0: load X, Z = I ------------------------------------------------------------
+    const cf* X = P.X + (size_t)job * P.x_stride;
+    for (int e = tid; e < nvp * LS; e += ST) {
+        int i = e / LS, c = e - i * LS;
+        Ys[e] = (i < nv && c < L) ? X[(size_t)i * L + c] : cf_make(0.f, 0.f);
+    }
+    for (int i = 0; i < nv; ++i) {
+        cf* zr = zrow(i);
+        for (int c = tid; c < ZS; c += ST) zr[c] = cf_make(c == i ? 1.f : 0.f, 0.f);
+    }
+    if (tid < 2) cnt[tid] = 0;
+    __syncthreads();
+
+    // ---- phase 1: Householder QR, one thread per column of [Y | Z] ---------------------------
+    const int J = min(nv - 1, L);
+    if (J > 0) {
+        if (warp == 0) {
+            float t2 = 0.f;
+            for (int i = lane; i < nv; i += 32) {
+                cf v = Ys[(size_t)i * LS];
+                vbuf[i] = v;
+                if (i > 0) t2 += cf_abs2(v);
+            }
+            t2 = warp_sum(t2);
+            if (lane == 0) { cf x0 = Ys[0]; scal[0] = x0.x; scal[1] = x0.y; scal[2] = t2; }
+        }
+        __syncthreads();
+        const bool isY = tid < L;
+        const bool isZ = !isY && (tid - L) < nv;
+        const int col = isY ? tid : tid - L;
+        for (int j = 0; j < J; ++j) {
+            const int cur = j & 1, nxt = cur ^ 1;
+            const cf* vb = vbuf + cur * nvp;
+            cf* vn = vbuf + nxt * nvp;
+            const cf x0 = cf_make(scal[cur * 4 + 0], scal[cur * 4 + 1]);
+            const float tail2 = scal[cur * 4 + 2];
+            const bool record = isY && (col == j + 1) && (j + 1 < J);
+            if (tail2 > 0.f) {
+                float ax0sq = cf_abs2(x0);
+                float ax0 = sqrtf(ax0sq);
+                float normx = sqrtf(tail2 + ax0sq);
+                cf ph = ax0 > 0.f ? cf_scale(1.0f / ax0, x0) : cf_make(1.f, 0.f);
+                cf alpha = cf_scale(-normx, ph);
+                cf v0 = cf_sub(x0, alpha);
+                float tau = 1.0f / (normx * (normx + ax0));
+                if (isY && col == j) {
+                    Ys[(size_t)j * LS + j] = alpha;
+                    for (int i = j + 1; i < nv; ++i) Ys[(size_t)i * LS + j] = cf_make(0.f, 0.f);
+                } else if ((isY && col > j) || isZ) {
+                    cf w;
+                    if (isY) {
+                        w = cf_fma_conja(v0, Ys[(size_t)j * LS + col], cf_make(0.f, 0.f));
+                        for (int i = j + 1; i < nv; ++i) w = cf_fma_conja(vb[i], Ys[(size_t)i * LS + col], w);
+                    } else {
+                        w = cf_fma_conja(v0, zrow(j)[col], cf_make(0.f, 0.f));
+                        for (int i = j + 1; i < nv; ++i) w = cf_fma_conja(vb[i], zrow(i)[col], w);
+                    }
+                    cf tw = cf_scale(-tau, w);
+                    float t2 = 0.f;
+                    if (isY) {
+                        cf* pj = &Ys[(size_t)j * LS + col];
+                        *pj = cf_fma(v0, tw, *pj);
+                        for (int i = j + 1; i < nv; ++i) {
+                            cf* pi = &Ys[(size_t)i * LS + col];
+                            cf nvl = cf_fma(vb[i], tw, *pi);
+                            *pi = nvl;
+                            if (record) { vn[i] = nvl; if (i > j + 1) t2 += cf_abs2(nvl); }
+                        }
+                    } else {
+                        cf* pj = &zrow(j)[col];
+                        *pj = cf_fma(v0, tw, *pj);
+                        for (int i = j + 1; i < nv; ++i) {
+                            cf* pi = &zrow(i)[col];
+                            *pi = cf_fma(vb[i], tw, *pi);
+                        }
+                    }
+                    if (record) {
+                        cf x0n = Ys[(size_t)(j + 1) * LS + col];
+                        scal[nxt * 4 + 0] = x0n.x; scal[nxt * 4 + 1] = x0n.y; scal[nxt * 4 + 2] = t2;
+                    }
+                }
+            } else if (record) {     // reflector skipped (column already reduced): H = I
+                float t2 = 0.f;
+                for (int i = j + 1; i < nv; ++i) {
+                    cf v = Ys[(size_t)i * LS + col];
+                    vn[i] = v;
+                    if (i > j + 1) t2 += cf_abs2(v);
+                }
+                cf x0n = Ys[(size_t)(j + 1) * LS + col];
+                scal[nxt * 4 + 0] = x0n.x; scal[nxt * 4 + 1] = x0n.y; scal[nxt * 4 + 2] = t2;
+            }
+            __syncthreads();
+        }
+    }
+
+    // ---- phase 2: one-sided Jacobi on the rows of Y ------------------------------------------
+    const int nact = min(nv, L);                   // rows >= L of R are exactly zero
+    const int nb = 2 * ((nact + 7) / 8);           // 4-row blocks (even count)
+    const int mcirc = nb - 1;
+    const int ngroups = nb / 2;
+    const int nrounds = nb > 2 ? nb - 1 : 1;
+    const int ylanes = P.LC / 32, zlanes = P.ZC / 32;
+    int sweeps = 0, status = 0;
+    if (nact >= 2) {
+        status = 1;
+        for (int sweep = 0; sweep < P.max_sweeps; ++sweep) {
+            int my_rot = 0;
+            for (int r = 0; r < nrounds; ++r) {
+                for (int g = warp; g < ngroups; g += NW) {
+                    int I, Jb;
+                    if (nb == 2) { I = 0; Jb = 1; }
+                    else if (g == 0) { I = mcirc; Jb = r; }
+                    else { I = (r + g) % mcirc; Jb = (r - g + mcirc) % mcirc; }
+                    int rows[8];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { rows[i] = 4 * I + i; rows[4 + i] = 4 * Jb + i; }
+                    cf y[8][EPL], z[8][EPL];
+                    float a[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const cf* yr = Ys + (size_t)rows[i] * LS;
+                        const bool zr_ok = rows[i] < nv;
+                        const cf* zr = zr_ok ? zrow(rows[i]) : Ys;
+                        float s2 = 0.f;
+#pragma unroll
+                        for (int t = 0; t < EPL; ++t) {
+                            y[i][t] = (t < ylanes) ? yr[lane + 32 * t] : cf_make(0.f, 0.f);
+                            z[i][t] = (zr_ok && t < zlanes) ? zr[lane + 32 * t] : cf_make(0.f, 0.f);
+                            s2 += cf_abs2(y[i][t]);
+                        }
+                        a[i] = s2;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
+                    int nrot = 0;
+                    if (r == 0) {
+                        { const int A_[4] = {0, 2, 4, 6}, B_[4] = {1, 3, 5, 7}; nrot += sub_round<4>(y, z, a, A_, B_, P.tol2); }
+                        { const int A_[4] = {0, 1, 4, 5}, B_[4] = {2, 3, 6, 7}; nrot += sub_round<4>(y, z, a, A_, B_, P.tol2); }
+                        { const int A_[4] = {0, 1, 4, 5}, B_[4] = {3, 2, 7, 6}; nrot += sub_round<4>(y, z, a, A_, B_, P.tol2); }
+                    }
+                    { const int A_[4] = {0, 1, 2, 3}, B_[4] = {4, 5, 6, 7}; nrot += sub_round<4>(y, z, a, A_, B_, P.tol2); }
+                    { const int A_[4] = {0, 1, 2, 3}, B_[4] = {5, 6, 7, 4}; nrot += sub_round<4>(y, z, a, A_, B_, P.tol2); }
+                    { const int A_[4] = {0, 1, 2, 3}, B_[4] = {6, 7, 4, 5}; nrot += sub_round<4>(y, z, a, A_, B_, P.tol2); }
+                    { const int A_[4] = {0, 1, 2, 3}, B_[4] = {7, 4, 5, 6}; nrot += sub_round<4>(y, z, a, A_, B_, P.tol2); }
+                    if (nrot) {
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            cf* yr = Ys + (size_t)rows[i] * LS;
+                            const bool zr_ok = rows[i] < nv;
+                            cf* zr = zr_ok ? zrow(rows[i]) : Ys;
+#pragma unroll
+                            for (int t = 0; t < EPL; ++t) {
+                                if (t < ylanes) yr[lane + 32 * t] = y[i][t];
+                                if (zr_ok && t < zlanes) zr[lane + 32 * t] = z[i][t];
+                            }
+                        }
+                        my_rot += nrot;
+                    }
+                }
+                __syncthreads();
+            }
+            if (lane == 0 && my_rot) atomicAdd(&cnt[sweep & 1], my_rot);
+            __syncthreads();
+            int total = cnt[sweep & 1];
+            if (tid == 0) cnt[(sweep + 1) & 1] = 0;
+            sweeps = sweep + 1;
+            if (total == 0) { status = 0; break; }
+            // the reset of the other counter is ordered before its next use by the barriers above
+        }
+    }
+
+    // ---- phase 3: singular values, stable descending sort, split/absorb -----------------------
+    __syncthreads();
+    for (int i = warp; i < nvp; i += NW) {
+        float s2 = 0.f;
+        if (i < nv) {
+            const cf* yr = Ys + (size_t)i * LS;
+            for (int c = lane; c < L; c += 32) s2 += cf_abs2(yr[c]);
+        }
+        s2 = warp_sum(s2);
+        if (lane == 0) { sig[i] = sqrtf(s2); perm[i] = i; }
+    }
+    __syncthreads();
+    int myrank = -1;
+    if (tid < nv) {
+        float si = sig[tid];
+        int rank = 0;
+        for (int j = 0; j < nv; ++j) {
+            float sj = sig[j];
+            rank += (sj > si) || (sj == si && j < tid);
+        }
+        myrank = rank;
+    }
+    __syncthreads();
+    if (myrank >= 0) perm[myrank] = tid;
+    __syncthreads();
+
+    const int k = P.k;
+    cf *left, *right; float* sv;
+    if (P.descs) {
+        int di = job / P.nbatch, bi = job % P.nbatch;
+        const mpsb_gate2_desc d = P.descs[di];
+        left = (cf*)d.out_l + (size_t)bi * d.bs_out_l;
+        right = (cf*)d.out_r + (size_t)bi * d.bs_out_r;
+        sv = d.svals ? d.svals + (size_t)bi * d.bs_svals : nullptr;
+    } else {
+        left = P.left + (size_t)job * P.left_stride;
+        right = P.right + (size_t)job * P.right_stride;
+        sv = P.svals ? P.svals + (size_t)job * P.svals_stride : nullptr;
+    }
+    if (P.lc) {
+        // right [k][L] = Y_k ; left [nv][k] = conj(Z_k)^T
+        for (int e = tid; e < k * L; e += ST) { int j = e / L, c = e - j * L; right[e] = Ys[(size_t)perm[j] * LS + c]; }
+        for (int e = tid; e < nv * k; e += ST) { int a_ = e / k, j = e - a_ * k; left[e] = cf_conj(zrow(perm[j])[a_]); }
+    } else {
+        // left [L][k] = Y_k^T ; right [k][nv] = conj(Z_k)
+        for (int e = tid; e < L * k; e += ST) { int a_ = e / k, j = e - a_ * k; left[e] = Ys[(size_t)perm[j] * LS + a_]; }
+        for (int e = tid; e < k * nv; e += ST) { int j = e / nv, b_ = e - j * nv; right[e] = cf_conj(zrow(perm[j])[b_]); }
+    }
+    if (sv) for (int j = tid; j < min(nv, L); j += ST) sv[j] = sig[perm[j]];
+    if (P.info && tid == 0) { P.info[2 * job] = status; P.info[2 * job + 1] = sweeps; }
+}
+
+struct Layout { int nvp, LC, LS, ZC, ZS, nz_smem; size_t smem; };
+
+Layout make_layout(int nv, int L) {
+    Layout lo;
+    lo.nvp = (nv + 7) / 8 * 8;
+    lo.LC = (L + 31) / 32 * 32; lo.LS = lo.LC + 1;
+    lo.ZC = (nv + 31) / 32 * 32; lo.ZS = lo.ZC + 1;
+    size_t fixed = (size_t)lo.nvp * lo.LS * 8 + (size_t)2 * lo.nvp * 8 + (size_t)lo.nvp * 8 + 8 * 4 + 2 * 4 + 64;
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || optin <= 0)
+        optin = 232448;      // sm_100: 227 KB (also the value assumed when planning without a device)
+    size_t avail = (size_t)optin > fixed ? (size_t)optin - fixed : 0;
+    size_t per_row = (size_t)lo.ZS * 8;
+    int fit = (int)(avail / per_row);
+    lo.nz_smem = fit >= nv ? nv : fit;
+    lo.smem = fixed + (size_t)lo.nz_smem * per_row;
+    return lo;
+}
+
+}  // namespace
+
+size_t svd_small_global_z_elems(int nv, int L) {
+    Layout lo = make_layout(nv, L);
+    return (size_t)(nv - lo.nz_smem) * lo.ZS;
+}
+
+int launch_svd_small(const cf* X, int64_t x_job_stride, int njobs, int nv, int L, int k,
+                     int left_canonical, const mpsb_gate2_desc* descs, int ndesc, int nbatch,
+                     cf* left, int64_t left_stride, cf* right, int64_t right_stride,
+                     float* svals, int64_t svals_stride, int32_t* info, cf* zglobal,
+                     cudaStream_t st) {
+    (void)ndesc;
+    if (njobs <= 0) return 0;
+    MPSB_ARG(nv >= 1 && L >= 1 && nv <= MPSB_MAX_SMALL_DIM && L <= MPSB_MAX_SMALL_DIM,
+             "svd_small: shape %d x %d outside [1, %d]", nv, L, MPSB_MAX_SMALL_DIM);
+    MPSB_ARG(k >= 0 && k <= (nv < L ? nv : L), "svd_small: k=%d out of range for %d x %d", k, nv, L);
+    Layout lo = make_layout(nv, L);
+    SvdSmallParams P;
+    P.X = X; P.x_stride = x_job_stride;
+    P.nv = nv; P.L = L; P.k = k; P.lc = left_canonical;
+    P.nvp = lo.nvp; P.LS = lo.LS; P.ZS = lo.ZS; P.LC = lo.LC; P.ZC = lo.ZC;
+    P.nz_smem = lo.nz_smem;
+    P.zg = zglobal; P.zg_stride = (int64_t)(nv - lo.nz_smem) * lo.ZS;
+    MPSB_ARG(P.zg_stride == 0 || zglobal != nullptr, "svd_small: Z spill workspace missing");
+    P.descs = descs; P.nbatch = nbatch > 0 ? nbatch : 1;
+    P.left = left; P.left_stride = left_stride; P.right = right; P.right_stride = right_stride;
+    P.svals = svals; P.svals_stride = svals_stride;
+    P.info = info;
+    P.max_sweeps = 30;
+    P.tol2 = 3e-6f * 3e-6f;
+    MPSB_CUDA(cudaFuncSetAttribute(svd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lo.smem));
+    svd_small_kernel<<<njobs, ST, lo.smem, st>>>(P);
+    MPSB_LAUNCH_CHECK("svd_small_kernel");
+    return 0;
+}

@@ -1,0 +1,328 @@
+"""Device-resident site-tensor store and plan execution.
+
+One ``DeviceChain`` holds ``nbatch`` independent MPS of identical shape (the single ``MPS``
+object is the ``nbatch == 1`` case).  All site tensors live in ONE complex64 slab in HBM:
+
+    slab[b, off_i : off_i + cap_i * d * cap_{i+1}]   holds site i of batch member b,
+    dense row-major [chi_i][d][chi_{i+1}] in the first chi_i*d*chi_{i+1} entries,
+
+where ``cap`` are bond capacities (the running maximum of each bond dimension, known
+statically from the plan, padded to chi = maxsvals in the bulk).  Gates are applied in
+place: the theta kernel writes to workspace before the split kernel overwrites the two
+sites.  Replaces the Python list of ``tn.Node`` of ``mpsim/core.py:190-243``.
+
+PyTorch is used only to own device memory and streams; every computation is a call into
+``libmpsim_b200.so`` (``include/mpsim_b200.h``).
+"""
+import ctypes
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from mpsim_b200 import _lib
+from mpsim_b200.planner import Plan
+
+MAX_JOBS_PER_CALL = 65535
+
+
+def _torch():
+    import torch
+    return torch
+
+
+class CompiledPlan:
+    """A plan bound to a chain's buffers: device descriptor tables + the launch list."""
+
+    def __init__(self) -> None:
+        self.launches: List[Tuple] = []
+        self.desc1 = None
+        self.desc2 = None
+        self.gates = None            # device [ngates][nb_g][width] complex64
+        self.gates_host = None       # pinned staging of the same shape
+        self.info = None             # device int32 [napps2 * B][2]
+        self.svals = None            # device float32 [napps2][B][maxmn] or None
+        self.svals_width = 0
+        self.order2: List[int] = []  # sorted position -> index into plan.apps2
+        self.workspace_bytes = 0
+        self.plan: Optional[Plan] = None
+        self.bonds_out: List[int] = []
+        self.n_launch_calls = 0
+
+
+class DeviceChain:
+    def __init__(self, nqudits: int, d: int = 2, nbatch: int = 1, device: Any = None,
+                 caps: Optional[Sequence[int]] = None) -> None:
+        torch = _torch()
+        _lib.load(require_device=True)
+        self.n = int(nqudits)
+        self.d = int(d)
+        self.B = int(nbatch)
+        self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self.bonds = [1] * (self.n + 1)
+        self.caps = [1] * (self.n + 1)
+        if caps is not None:
+            self.caps = [max(1, int(c)) for c in caps]
+            self.caps[0] = self.caps[-1] = 1
+        self._alloc(self.caps)
+        self._workspace = None
+        self.reset()
+
+    # ------------------------------------------------------------------ layout
+    def _offsets(self, caps: Sequence[int]) -> Tuple[List[int], int]:
+        offs, total = [], 0
+        for i in range(self.n):
+            offs.append(total)
+            elems = caps[i] * self.d * caps[i + 1]
+            total += (elems + 15) // 16 * 16          # 128-byte aligned slots
+        return offs, max(total, 16)
+
+    def _alloc(self, caps: Sequence[int]) -> None:
+        torch = _torch()
+        self.caps = list(caps)
+        self.offs, self.total = self._offsets(self.caps)
+        self.slab = torch.zeros((self.B, self.total), dtype=torch.complex64, device=self.device)
+
+    def ensure_caps(self, caps: Sequence[int]) -> None:
+        """Grow bond capacities (re-lays the slab out and copies the live tensors)."""
+        new = [max(a, b) for a, b in zip(self.caps, caps)]
+        if new == self.caps:
+            return
+        old_slab, old_offs = self.slab, self.offs
+        self._alloc(new)
+        for i in range(self.n):
+            ne = self.bonds[i] * self.d * self.bonds[i + 1]
+            if ne:
+                self.slab[:, self.offs[i]:self.offs[i] + ne] = old_slab[:, old_offs[i]:old_offs[i] + ne]
+
+    def reset(self) -> None:
+        """|0...0> on every batch member (``mpsim/core.py:190-218``)."""
+        self.bonds = [1] * (self.n + 1)
+        self.slab.zero_()
+        idx = _torch().tensor(self.offs, device=self.device, dtype=_torch().long)
+        self.slab[:, idx] = 1.0
+
+    def site_elems(self, i: int) -> int:
+        return self.bonds[i] * self.d * self.bonds[i + 1]
+
+    def site_ptr(self, i: int) -> int:
+        return self.slab.data_ptr() + self.offs[i] * 8
+
+    def site_view(self, i: int, b: int = 0):
+        ne = self.site_elems(i)
+        return self.slab[b, self.offs[i]:self.offs[i] + ne].view(self.bonds[i], self.d, self.bonds[i + 1])
+
+    def set_site(self, i: int, tensor, b: Optional[int] = None) -> None:
+        """Overwrite site i (all batch members, or one) with a [chiL][d][chiR] tensor."""
+        torch = _torch()
+        t = torch.as_tensor(tensor).to(device=self.device, dtype=torch.complex64).contiguous()
+        cl, d, cr = t.shape
+        assert d == self.d
+        bonds = list(self.bonds)
+        bonds[i], bonds[i + 1] = cl, cr
+        self.ensure_caps(bonds)
+        self.bonds = bonds
+        ne = cl * d * cr
+        if b is None:
+            self.slab[:, self.offs[i]:self.offs[i] + ne] = t.reshape(1, -1)
+        else:
+            self.slab[b, self.offs[i]:self.offs[i] + ne] = t.reshape(-1)
+
+    def clone(self) -> "DeviceChain":
+        new = DeviceChain.__new__(DeviceChain)
+        new.n, new.d, new.B, new.device = self.n, self.d, self.B, self.device
+        new.bonds, new.caps = list(self.bonds), list(self.caps)
+        new.offs, new.total = list(self.offs), self.total
+        new.slab = self.slab.clone()
+        new._workspace = None
+        return new
+
+    def _site_refs(self) -> np.ndarray:
+        refs = np.zeros(self.n, dtype=_lib.SITE_REF)
+        for i in range(self.n):
+            refs[i] = (self.site_ptr(i), self.total, self.bonds[i], self.bonds[i + 1])
+        return refs
+
+    def workspace(self, nbytes: int):
+        torch = _torch()
+        nbytes = max(int(nbytes), 256)
+        if self._workspace is None or self._workspace.numel() < nbytes:
+            self._workspace = None
+            self._workspace = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        return self._workspace
+
+    # ------------------------------------------------------------------ plan compilation
+    def compile(self, plan: Plan, per_batch_gates: bool = False, record_svals: bool = False) -> CompiledPlan:
+        """Bind ``plan`` (made against the chain's current bonds) to this chain's buffers."""
+        torch = _torch()
+        lib = _lib.load(require_device=True)
+        assert plan.bonds_in == self.bonds, "plan was made for different bond dimensions"
+        self.ensure_caps(plan.caps)
+        cp = CompiledPlan()
+        cp.plan = plan
+        cp.bonds_out = list(plan.bonds)
+        d, B = self.d, self.B
+        width = d ** 4
+        nb_g = B if per_batch_gates else 1
+        ng = len(plan.gates)
+        cp.gates = torch.zeros((max(ng, 1), nb_g, width), dtype=torch.complex64, device=self.device)
+        cp.gates_host = torch.zeros((max(ng, 1), nb_g, width), dtype=torch.complex64).pin_memory()
+        gbase = cp.gates.data_ptr()
+        gstride = nb_g * width * 8
+        bs_gate = width if per_batch_gates else 0
+
+        layers = plan.layers()
+        n1, n2 = len(plan.apps1), len(plan.apps2)
+        d1 = np.zeros(max(n1, 1), dtype=_lib.GATE1_DESC)
+        d2 = np.zeros(max(n2, 1), dtype=_lib.GATE2_DESC)
+        maxmn = max([min(d * a.chiL, d * a.chiR) for a in plan.apps2] + [1])
+        if record_svals and n2:
+            cp.svals = torch.zeros((n2, B, maxmn), dtype=torch.float32, device=self.device)
+            cp.svals_width = maxmn
+        cp.info = torch.zeros((max(n2, 1) * B, 2), dtype=torch.int32, device=self.device)
+        # bonds evolve layer by layer; replay them to know each 1q application's shape
+        bonds = list(plan.bonds_in)
+        p1 = p2 = 0
+        ws_need = 0
+        launches = []
+        for layer in layers:
+            if layer["one"]:
+                start = p1
+                max_elems = 1
+                for idx in layer["one"]:
+                    a = plan.apps1[idx]
+                    ptr = self.site_ptr(a.site)
+                    d1[p1] = (ptr, ptr, gbase + a.gate_index * gstride, self.total, self.total, bs_gate,
+                              bonds[a.site], bonds[a.site + 1])
+                    max_elems = max(max_elems, bonds[a.site] * d * bonds[a.site + 1])
+                    p1 += 1
+                launches.append(("g1", start, p1 - start, max_elems))
+            for key, idxs in layer["two"].items():
+                chiL, chiM, chiR, k, lc = key
+                start = p2
+                for idx in idxs:
+                    a = plan.apps2[idx]
+                    pl, pr = self.site_ptr(a.site), self.site_ptr(a.site + 1)
+                    sv = cp.svals.data_ptr() + p2 * B * maxmn * 4 if cp.svals is not None else 0
+                    d2[p2] = (pl, pr, pl, pr, gbase + a.gate_index * gstride, sv,
+                              self.total, self.total, self.total, self.total, bs_gate, maxmn)
+                    cp.order2.append(idx)
+                    p2 += 1
+                count = p2 - start
+                per_call = max(1, MAX_JOBS_PER_CALL // B)
+                for c0 in range(0, count, per_call):
+                    c = min(per_call, count - c0)
+                    launches.append(("g2", start + c0, c, chiL, chiM, chiR, k, int(lc)))
+                    ws_need = max(ws_need, lib.mpsb_gate2_workspace_bytes(c, B, d, chiL, chiM, chiR, k))
+            # bonds after this layer
+            for key, idxs in layer["two"].items():
+                for idx in idxs:
+                    a = plan.apps2[idx]
+                    bonds[a.site + 1] = a.k
+        cp.desc1 = _lib.to_device_bytes(d1, self.device)
+        cp.desc2 = _lib.to_device_bytes(d2, self.device)
+        cp.launches = launches
+        cp.workspace_bytes = int(ws_need)
+        cp.slab_ptr = self.slab.data_ptr()
+        # stage the gates of the plan itself (callers may overwrite cp.gates_host and re-upload)
+        tab = plan.gate_table(width)
+        if ng:
+            cp.gates_host[:ng] = torch.from_numpy(tab).unsqueeze(1)
+        return cp
+
+    def upload_gates(self, cp: CompiledPlan) -> None:
+        cp.gates.copy_(cp.gates_host, non_blocking=True)
+
+    def run(self, cp: CompiledPlan, upload: bool = True) -> None:
+        """Launch a compiled plan on the current stream (asynchronous)."""
+        lib = _lib.load(require_device=True)
+        assert cp.slab_ptr == self.slab.data_ptr(), "chain buffers moved since the plan was compiled"
+        if upload:
+            self.upload_gates(cp)
+        ws = self.workspace(cp.workspace_bytes)
+        st = _lib.stream_ptr()
+        d, B = self.d, self.B
+        p1, p2, pi = cp.desc1.data_ptr(), cp.desc2.data_ptr(), cp.info.data_ptr()
+        for L in cp.launches:
+            if L[0] == "g1":
+                _, off, cnt, max_elems = L
+                _lib.check(lib.mpsb_apply_gate1(p1 + off * _lib.GATE1_DESC.itemsize, cnt, B, d, max_elems, st),
+                           "mpsb_apply_gate1")
+            else:
+                _, off, cnt, chiL, chiM, chiR, k, lc = L
+                _lib.check(lib.mpsb_apply_gate2(p2 + off * _lib.GATE2_DESC.itemsize, cnt, B, d, chiL, chiM, chiR,
+                                                k, lc, ws.data_ptr(), ws.numel(), pi + off * B * 8, st),
+                           "mpsb_apply_gate2")
+        cp.n_launch_calls = len(cp.launches)
+        self.bonds = list(cp.bonds_out)
+
+    # ------------------------------------------------------------------ whole-chain contractions
+    def inner_products(self, other: Optional["DeviceChain"] = None):
+        """<self|other> per batch member (sum self * conj(other), ``mpsim/core.py:543-561``):
+        device complex64 [B]."""
+        torch = _torch()
+        lib = _lib.load(require_device=True)
+        other = self if other is None else other
+        if min(self.bonds) == 0 or min(other.bonds) == 0:
+            return torch.zeros(self.B, dtype=torch.complex64, device=self.device)
+        a, b = self._site_refs(), other._site_refs()
+        need = lib.mpsb_inner_workspace_bytes(self.B, self.d, max(self.bonds), max(other.bonds))
+        ws = self.workspace(need)
+        out = torch.empty(self.B, dtype=torch.complex64, device=self.device)
+        _lib.check(lib.mpsb_inner_products(a.ctypes.data, b.ctypes.data, self.n, self.B, self.d, out.data_ptr(),
+                                           ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "mpsb_inner_products")
+        return out
+
+    def norms(self):
+        """device float32 [B]: sqrt(Re <psi|psi>)  (``mpsim/core.py:563-565``)."""
+        torch = _torch()
+        return torch.sqrt(torch.clamp(self.inner_products().real, min=0.0))
+
+    def scale(self, factors) -> None:
+        """site <- factors[b] * site for all sites (``mpsim/core.py:590-594``)."""
+        torch = _torch()
+        lib = _lib.load(require_device=True)
+        f = torch.as_tensor(factors, dtype=torch.float32, device=self.device).contiguous()
+        refs = _lib.to_device_bytes(self._site_refs(), self.device)
+        max_elems = max(self.site_elems(i) for i in range(self.n))
+        # the call is limited to 65535 (site, batch) jobs: chunk over sites
+        per = max(1, MAX_JOBS_PER_CALL // self.B)
+        for s0 in range(0, self.n, per):
+            c = min(per, self.n - s0)
+            _lib.check(lib.mpsb_scale_sites(refs.data_ptr() + s0 * _lib.SITE_REF.itemsize, c, self.B, self.d,
+                                            f.data_ptr(), max(max_elems, 1), _lib.stream_ptr()), "mpsb_scale_sites")
+
+    def wavefunction(self, b: int = 0):
+        """device complex64 [d**n], big-endian (``mpsim/core.py:483-500``)."""
+        torch = _torch()
+        lib = _lib.load(require_device=True)
+        refs = self._site_refs()
+        need = lib.mpsb_wavefunction_workspace_bytes(refs.ctypes.data, self.n, self.d)
+        ws = self.workspace(need)
+        out = torch.empty(self.d ** self.n, dtype=torch.complex64, device=self.device)
+        _lib.check(lib.mpsb_wavefunction(refs.ctypes.data, self.n, self.d, int(b), out.data_ptr(), ws.data_ptr(),
+                                         ws.numel(), _lib.stream_ptr()), "mpsb_wavefunction")
+        return out
+
+    def amplitudes(self, bitstrings):
+        """device complex64 [B][nbits]: <bits|psi_b> for each row of ``bitstrings`` (nbits x n)."""
+        torch = _torch()
+        lib = _lib.load(require_device=True)
+        bits = np.ascontiguousarray(np.asarray(bitstrings, dtype=np.uint8).reshape(-1, self.n))
+        if bits.size and bits.max() >= self.d:
+            raise ValueError("basis state digit out of range for the qudit dimension")
+        nbits = bits.shape[0]
+        out = torch.zeros((self.B, nbits), dtype=torch.complex64, device=self.device)
+        if nbits == 0 or min(self.bonds) == 0:
+            return out
+        bits_dev = torch.from_numpy(bits).to(self.device)
+        refs = _lib.to_device_bytes(self._site_refs(), self.device)
+        for b0 in range(0, self.B, MAX_JOBS_PER_CALL):
+            nb = min(MAX_JOBS_PER_CALL, self.B - b0)
+            # batch offset folded into the site pointers through a shifted copy of the refs
+            r = self._site_refs()
+            r["site"] += np.uint64(b0 * self.total * 8)
+            rdev = refs if b0 == 0 else _lib.to_device_bytes(r, self.device)
+            _lib.check(lib.mpsb_amplitudes(rdev.data_ptr(), self.n, nb, self.d, max(self.bonds), bits_dev.data_ptr(),
+                                           nbits, out.data_ptr() + b0 * nbits * 8, _lib.stream_ptr()),
+                       "mpsb_amplitudes")
+        return out

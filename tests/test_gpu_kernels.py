@@ -1,0 +1,139 @@
+"""GPU: each kernel through the C-ABI against numpy on the same seeded inputs."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _rand(rng, *shape):
+    return (rng.randn(*shape) + 1j * rng.randn(*shape)).astype(np.complex64)
+
+
+def _graded(rng, m, n, decay):
+    a = rng.randn(m, n) + 1j * rng.randn(m, n)
+    u, s, vh = np.linalg.svd(a, full_matrices=False)
+    s = s * np.exp(-np.arange(len(s)) / len(s) * decay)
+    return ((u * s) @ vh).astype(np.complex64)
+
+
+def _svd(mats, k, lc):
+    import torch
+    from mpsim_b200 import _lib
+    lib = _lib.load(require_device=True)
+    mats = np.ascontiguousarray(mats, dtype=np.complex64)
+    nj, m, n = mats.shape
+    dev = torch.device("cuda")
+    x = torch.from_numpy(mats).to(dev)
+    left = torch.zeros((nj, m, k), dtype=torch.complex64, device=dev)
+    right = torch.zeros((nj, k, n), dtype=torch.complex64, device=dev)
+    sv = torch.zeros((nj, min(m, n)), dtype=torch.float32, device=dev)
+    info = torch.full((nj, 2), -1, dtype=torch.int32, device=dev)
+    ws = torch.empty(max(lib.mpsb_svd_workspace_bytes(nj, m, n), 256), dtype=torch.uint8, device=dev)
+    _lib.check(lib.mpsb_svd(x.data_ptr(), nj, m, n, k, int(lc), left.data_ptr(), right.data_ptr(), sv.data_ptr(),
+                            info.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()), "mpsb_svd")
+    torch.cuda.synchronize()
+    return left.cpu().numpy(), right.cpu().numpy(), sv.cpu().numpy(), info.cpu().numpy()
+
+
+@pytest.mark.parametrize("M,N,K", [(1, 1, 1), (7, 5, 3), (64, 64, 64), (130, 67, 33), (256, 128, 512)])
+def test_cgemm(M, N, K):
+    import torch
+    from mpsim_b200 import _lib
+    lib = _lib.load(require_device=True)
+    rng = np.random.RandomState(M * 1000 + N)
+    nb = 3
+    a, b = _rand(rng, nb, M, K), _rand(rng, nb, K, N)
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    dc = torch.zeros((nb, M, N), dtype=torch.complex64, device="cuda")
+    _lib.check(lib.mpsb_cgemm(da.data_ptr(), K, 1, 0, M * K, db.data_ptr(), N, 1, 0, K * N, dc.data_ptr(), N, M * N,
+                              M, N, K, nb, _lib.stream_ptr()))
+    ref = a.astype(np.complex128) @ b.astype(np.complex128)
+    np.testing.assert_allclose(dc.cpu().numpy(), ref, atol=2e-5 * np.sqrt(K) * 4)
+    # A^H B with strides: A stored [K][M]
+    at = np.ascontiguousarray(np.conj(np.transpose(a, (0, 2, 1))))
+    dat = torch.from_numpy(at).cuda()
+    _lib.check(lib.mpsb_cgemm(dat.data_ptr(), 1, M, 1, M * K, db.data_ptr(), N, 1, 0, K * N, dc.data_ptr(), N, M * N,
+                              M, N, K, nb, _lib.stream_ptr()))
+    np.testing.assert_allclose(dc.cpu().numpy(), ref, atol=2e-5 * np.sqrt(K) * 4)
+
+
+@pytest.mark.parametrize("shape", [(2, 2), (4, 2), (2, 8), (8, 8), (16, 32), (32, 16), (64, 64), (128, 64),
+                                   (64, 128), (100, 36), (128, 128)])
+@pytest.mark.parametrize("lc", [1, 0])
+def test_svd_small_matches_lapack(shape, lc):
+    m, n = shape
+    rng = np.random.RandomState(m * 131 + n * 7 + lc)
+    mats = np.stack([_graded(rng, m, n, 0.0), _graded(rng, m, n, 10.0), _graded(rng, m, n, 30.0)])
+    k = min(m, n)
+    left, right, sv, info = _svd(mats, k, lc)
+    assert (info[:, 0] == 0).all(), info
+    assert (info[:, 1] <= 14).all(), info
+    for j in range(len(mats)):
+        sref = np.linalg.svd(mats[j].astype(np.complex128), compute_uv=False)
+        assert np.abs(sv[j] - sref).max() <= 1e-5 * sref[0]            # north_star: 1e-5 relative
+        np.testing.assert_allclose(left[j] @ right[j], mats[j], atol=3e-6 * sref[0])
+        iso = left[j] if lc else right[j].conj().T
+        np.testing.assert_allclose(iso.conj().T @ iso, np.eye(k), atol=2e-5)
+    # truncated: exact projection onto the leading singular subspace
+    kk = max(1, k // 2)
+    left, right, sv, info = _svd(mats, kk, lc)
+    for j in range(len(mats)):
+        u, s, vh = np.linalg.svd(mats[j].astype(np.complex128), full_matrices=False)
+        best = (u[:, :kk] * s[:kk]) @ vh[:kk]
+        gap = s[kk - 1] - s[kk] if kk < len(s) else s[kk - 1]
+        tol = 1e-5 * s[0] * (1 + s[0] / max(gap, 1e-3 * s[0]) * 0.05)
+        np.testing.assert_allclose(left[j] @ right[j], best, atol=10 * tol)
+
+
+def test_svd_ties_and_rank_deficiency():
+    # Bell + maxsvals=1 (README.md:48-53): diagonal with a tie keeps the FIRST
+    m = np.diag([2 ** -0.5, 2 ** -0.5]).astype(np.complex64)[None]
+    for lc in (1, 0):
+        left, right, sv, info = _svd(m, 1, lc)
+        np.testing.assert_allclose(left[0] @ right[0], np.diag([2 ** -0.5, 0]), atol=1e-7)
+    # zero singular values are kept with an orthonormal isometry (core_test.py:932-944)
+    z = np.zeros((1, 8, 8), np.complex64)
+    z[0, 0, 0] = 1
+    z[0, 3, 5] = 0.5
+    for lc in (1, 0):
+        left, right, sv, info = _svd(z, 8, lc)
+        np.testing.assert_allclose(sv[0], [1, 0.5, 0, 0, 0, 0, 0, 0], atol=1e-7)
+        iso = left[0] if lc else right[0].conj().T
+        np.testing.assert_allclose(iso.conj().T @ iso, np.eye(8), atol=1e-6)
+        np.testing.assert_allclose(left[0] @ right[0], z[0], atol=1e-7)
+    # all-zero matrix
+    left, right, sv, info = _svd(np.zeros((1, 4, 4), np.complex64), 4, 1)
+    assert np.all(sv == 0) and np.all(np.isfinite(left)) and np.all(np.isfinite(right))
+
+
+def test_svd_batch_of_128x128():
+    rng = np.random.RandomState(9)
+    mats = np.stack([_graded(rng, 128, 128, d) for d in (0.0, 5.0, 20.0, 40.0, 0.0, 10.0)])
+    left, right, sv, info = _svd(mats, 64, 1)
+    assert (info[:, 0] == 0).all()
+    for j in range(len(mats)):
+        sref = np.linalg.svd(mats[j].astype(np.complex128), compute_uv=False)
+        assert np.abs(sv[j] - sref).max() <= 1e-5 * sref[0]
+        np.testing.assert_allclose(left[j].conj().T @ left[j], np.eye(64), atol=2e-5)
+
+
+@pytest.mark.parametrize("chi", [(1, 1, 1), (2, 1, 2), (4, 8, 2), (16, 16, 16), (33, 17, 40), (64, 64, 64)])
+@pytest.mark.parametrize("d", [2, 3])
+def test_theta(chi, d):
+    import torch
+    from mpsim_b200 import _lib
+    lib = _lib.load(require_device=True)
+    cl, cm, cr = chi
+    rng = np.random.RandomState(cl * 7 + cm * 3 + cr + d)
+    nb = 3
+    A, B = _rand(rng, nb, cl, d, cm), _rand(rng, nb, cm, d, cr)
+    G = _rand(rng, nb, d, d, d, d)
+    dA, dB, dG = (torch.from_numpy(x).cuda() for x in (A, B, G))
+    desc = np.zeros(1, dtype=_lib.GATE2_DESC)
+    desc[0] = (dA.data_ptr(), dB.data_ptr(), 0, 0, dG.data_ptr(), 0, cl * d * cm, cm * d * cr, 0, 0, d ** 4, 0)
+    ddesc = _lib.to_device_bytes(desc, "cuda")
+    out = torch.zeros((nb, d * cl, d * cr), dtype=torch.complex64, device="cuda")
+    _lib.check(lib.mpsb_theta(ddesc.data_ptr(), 1, nb, d, cl, cm, cr, out.data_ptr(), None, 0, _lib.stream_ptr()))
+    ref = np.einsum("bxypq,blpm,bmqr->blxyr", G.astype(np.complex128), A.astype(np.complex128), B.astype(np.complex128))
+    ref = ref.reshape(nb, cl * d, d * cr)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, atol=3e-5 * np.sqrt(cm) * 4)
