@@ -22,6 +22,7 @@
 //        otherwise      : left  = Y_k^T   (U.S)   right = conj(Z_k) (Vh)
 //      left.right == exact rank-k projection of theta whether or not Jacobi converged.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -39,7 +40,7 @@ struct SvdSmallParams {
     cf* left; int64_t left_stride; cf* right; int64_t right_stride;   // output mode B
     float* svals; int64_t svals_stride;
     int32_t* info;
-    int max_sweeps; float tol2;
+    int max_sweeps; float tol2; int do_qr;
 };
 
 __device__ __forceinline__ void rot_params(float a, float b, float gr, float gi, float g2,
@@ -133,11 +134,29 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
     const int nzs = P.nz_smem;
     auto zrow = [&](int i) -> cf* { return i < nzs ? Zs + (size_t)i * ZS : zg + (size_t)(i - nzs) * ZS; };
 
-    // ---- phase 0: load X, Z = I ------------------------------------------------------------
+    // ---- phase 0: load X scaled by an exact power of two so that max|x| is in [1, 2), Z = I ----
+    // (the guards below are absolute, and products of numerical zeros would otherwise
+    //  underflow in the Gram entries; LAPACK scales for the same reason)
     const cf* X = P.X + (size_t)job * P.x_stride;
+    float mx = 0.f;
+    for (int e = tid; e < nv * L; e += ST) { cf v = X[e]; mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) scal[warp] = mx;
+    __syncthreads();
+    mx = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) mx = fmaxf(mx, scal[w]);
+    int ex = 0;
+    if (mx > 0.f && isfinite(mx)) (void)frexpf(mx, &ex);      // mx = f * 2^ex, f in [0.5, 1)
+    const float scale_in = mx > 0.f ? ldexpf(1.0f, 1 - ex) : 1.0f;
+    const float scale_out = mx > 0.f ? ldexpf(1.0f, ex - 1) : 1.0f;
+    __syncthreads();
     for (int e = tid; e < nvp * LS; e += ST) {
         int i = e / LS, c = e - i * LS;
-        Ys[e] = (i < nv && c < L) ? X[(size_t)i * L + c] : cf_make(0.f, 0.f);
+        cf v = cf_make(0.f, 0.f);
+        if (i < nv && c < L) { v = X[(size_t)i * L + c]; v.x *= scale_in; v.y *= scale_in; }
+        Ys[e] = v;
     }
     for (int i = 0; i < nv; ++i) {
         cf* zr = zrow(i);
@@ -147,7 +166,7 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
     __syncthreads();
 
     // ---- phase 1: Householder QR, one thread per column of [Y | Z] ---------------------------
-    const int J = min(nv - 1, L);
+    const int J = P.do_qr ? min(nv - 1, L) : 0;
     if (J > 0) {
         if (warp == 0) {
             float t2 = 0.f;
@@ -167,11 +186,17 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
             const int cur = j & 1, nxt = cur ^ 1;
             const cf* vb = vbuf + cur * nvp;
             cf* vn = vbuf + nxt * nvp;
-            const cf x0 = cf_make(scal[cur * 4 + 0], scal[cur * 4 + 1]);
+            cf x0 = cf_make(scal[cur * 4 + 0], scal[cur * 4 + 1]);
             const float tail2 = scal[cur * 4 + 2];
             const bool record = isY && (col == j + 1) && (j + 1 < J);
-            if (tail2 > 0.f) {
-                float ax0sq = cf_abs2(x0);
+            float ax0sq = cf_abs2(x0);
+            // |x0|^2 below ~1e-30 is a denormal-range number with few significant bits: the
+            // phase x0/|x0| would be off by 1e-4 and the reflector no longer unitary (seen on
+            // GHZ circuits).  The matrix is scaled to max|x| in [1,2), so such an x0 is noise.
+            if (ax0sq < 1e-30f) { x0 = cf_make(0.f, 0.f); ax0sq = 0.f; }
+            // skip the reflector when the column is already reduced, or so small that
+            // 1/|x|^2 would overflow (QR is only a preconditioner: any unitary Z is valid)
+            if (tail2 > 0.f && tail2 + ax0sq > 1e-30f) {
                 float ax0 = sqrtf(ax0sq);
                 float normx = sqrtf(tail2 + ax0sq);
                 cf ph = ax0 > 0.f ? cf_scale(1.0f / ax0, x0) : cf_make(1.f, 0.f);
@@ -229,7 +254,7 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
     }
 
     // ---- phase 2: one-sided Jacobi on the rows of Y ------------------------------------------
-    const int nact = min(nv, L);                   // rows >= L of R are exactly zero
+    const int nact = P.do_qr ? min(nv, L) : nv;    // rows >= L of R are exactly zero
     const int nb = 2 * ((nact + 7) / 8);           // 4-row blocks (even count)
     const int mcirc = nb - 1;
     const int ngroups = nb / 2;
@@ -347,14 +372,14 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
     }
     if (P.lc) {
         // right [k][L] = Y_k ; left [nv][k] = conj(Z_k)^T
-        for (int e = tid; e < k * L; e += ST) { int j = e / L, c = e - j * L; right[e] = Ys[(size_t)perm[j] * LS + c]; }
+        for (int e = tid; e < k * L; e += ST) { int j = e / L, c = e - j * L; right[e] = cf_scale(scale_out, Ys[(size_t)perm[j] * LS + c]); }
         for (int e = tid; e < nv * k; e += ST) { int a_ = e / k, j = e - a_ * k; left[e] = cf_conj(zrow(perm[j])[a_]); }
     } else {
         // left [L][k] = Y_k^T ; right [k][nv] = conj(Z_k)
-        for (int e = tid; e < L * k; e += ST) { int a_ = e / k, j = e - a_ * k; left[e] = Ys[(size_t)perm[j] * LS + a_]; }
+        for (int e = tid; e < L * k; e += ST) { int a_ = e / k, j = e - a_ * k; left[e] = cf_scale(scale_out, Ys[(size_t)perm[j] * LS + a_]); }
         for (int e = tid; e < k * nv; e += ST) { int j = e / nv, b_ = e - j * nv; right[e] = cf_conj(zrow(perm[j])[b_]); }
     }
-    if (sv) for (int j = tid; j < min(nv, L); j += ST) sv[j] = sig[perm[j]];
+    if (sv) for (int j = tid; j < min(nv, L); j += ST) sv[j] = scale_out * sig[perm[j]];
     if (P.info && tid == 0) { P.info[2 * job] = status; P.info[2 * job + 1] = sweeps; }
 }
 
@@ -409,6 +434,10 @@ int launch_svd_small(const cf* X, int64_t x_job_stride, int njobs, int nv, int L
     P.info = info;
     P.max_sweeps = 30;
     P.tol2 = 3e-6f * 3e-6f;
+    P.do_qr = 1;
+    // debugging knobs (not part of the ABI)
+    if (const char* e = getenv("MPSB_SVD_MAX_SWEEPS")) P.max_sweeps = atoi(e);
+    if (const char* e = getenv("MPSB_SVD_NO_QR")) P.do_qr = atoi(e) ? 0 : 1;
     MPSB_CUDA(cudaFuncSetAttribute(svd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lo.smem));
     svd_small_kernel<<<njobs, ST, lo.smem, st>>>(P);
     MPSB_LAUNCH_CHECK("svd_small_kernel");

@@ -34,20 +34,27 @@ CROSS = [[(i, 4 + (i + s) % 4) for i in range(4)] for s in range(4)]
 
 def householder_qr(Y, Z, m):
     """In place: Y[:m] <- R (upper triangular), Z <- H_k ... H_1 Z.  Reflectors are skipped
-    when the column is already zero below the diagonal (keeps diagonal inputs untouched)."""
+    when the column is already zero below the diagonal (keeps diagonal inputs untouched) or so
+    small that 1/|x|^2 would overflow; a diagonal entry with |x0|^2 < 1e-30 is treated as 0
+    (its square is a denormal with few significant bits -- the phase x0/|x0| computed from it
+    made one reflector of a GHZ circuit non-unitary by 2e-4 on the GPU)."""
     L = Y.shape[1]
     for j in range(min(m - 1, L)):
         x = Y[j:m, j].copy()
         tail2 = F((np.abs(x[1:]) ** 2).sum())
-        if tail2 == 0:
-            continue
         x0 = x[0]
-        normx = F(np.sqrt(tail2 + F(abs(x0) ** 2)))
-        phase = C(x0 / abs(x0)) if abs(x0) > 0 else C(1)
+        ax0sq = F(F(x0.real) * F(x0.real) + F(x0.imag) * F(x0.imag))
+        if ax0sq < F(1e-30):
+            x0, ax0sq = C(0), F(0)
+        if not (tail2 > 0 and F(tail2 + ax0sq) > F(1e-30)):
+            continue
+        ax0 = F(np.sqrt(ax0sq))
+        normx = F(np.sqrt(F(tail2 + ax0sq)))
+        phase = C(x0 * F(F(1) / ax0)) if ax0 > 0 else C(1)
         alpha = C(-phase * normx)
         v = x.copy()
         v[0] = x0 - alpha
-        tau = F(1.0) / F(normx * (normx + abs(x0)))      # 2 / ||v||^2
+        tau = F(1.0) / F(normx * F(normx + ax0))      # 2 / ||v||^2
         for A in (Y, Z):
             w = np.conj(v) @ A[j:m, :]
             A[j:m, :] -= np.outer(tau * v, w).astype(C)

@@ -137,3 +137,30 @@ def test_theta(chi, d):
     ref = np.einsum("bxypq,blpm,bmqr->blxyr", G.astype(np.complex128), A.astype(np.complex128), B.astype(np.complex128))
     ref = ref.reshape(nb, cl * d, d * cr)
     np.testing.assert_allclose(out.cpu().numpy(), ref, atol=3e-5 * np.sqrt(cm) * 4)
+
+
+@pytest.mark.parametrize("scale", [1e-18, 1e-9, 1e6])
+def test_svd_is_scale_robust(scale):
+    """Tiny / huge entries (products of numerical zeros appear in structured circuits) must not
+    overflow the Householder or rotation formulas."""
+    rng = np.random.RandomState(3)
+    mats = np.stack([_graded(rng, 16, 16, 5.0), _graded(rng, 16, 16, 60.0)]) * np.float32(scale)
+    mats[1, :, 3] = 0
+    mats[1, 5, :] *= np.float32(1e-12)
+    for lc in (1, 0):
+        left, right, sv, info = _svd(mats.astype(np.complex64), 16, lc)
+        assert np.all(np.isfinite(left)) and np.all(np.isfinite(right)) and np.all(np.isfinite(sv))
+        for j in range(2):
+            sref = np.linalg.svd(mats[j].astype(np.complex128), compute_uv=False)
+            assert np.abs(sv[j] - sref).max() <= 1e-5 * sref[0]
+            np.testing.assert_allclose(left[j] @ right[j], mats[j], atol=3e-6 * sref[0])
+
+
+def test_svd_denormal_diagonal_regression():
+    import os
+    M = np.load(os.path.join(os.path.dirname(__file__), "golden", "ghz_theta_16x8.npy"))
+    for lc in (1, 0):
+        left, right, sv, info = _svd(M[None], 8, lc)
+        np.testing.assert_allclose(left[0] @ right[0], M, atol=1e-6)
+        iso = left[0] if lc else right[0].conj().T
+        np.testing.assert_allclose(iso.conj().T @ iso, np.eye(8), atol=2e-6)

@@ -71,3 +71,15 @@ def test_rank_deficient_keeps_orthonormal_isometry():      # core_test.py:932-94
         iso = lft if left else rgt.conj().T
         np.testing.assert_allclose(iso.conj().T @ iso, np.eye(4), atol=1e-6)
         np.testing.assert_allclose(lft @ rgt, M, atol=1e-7)
+
+
+def test_denormal_diagonal_entry_regression():
+    """theta of a GHZ circuit (16x8, four singular values ~1, four ~1e-8) on which a
+    denormal |x0|^2 made one Householder reflector non-unitary by 2e-4."""
+    import os
+    M = np.load(os.path.join(os.path.dirname(__file__), "golden", "ghz_theta_16x8.npy"))
+    for left in (True, False):
+        lft, rgt, sig, _ = jm.split(M, 8, left)
+        np.testing.assert_allclose(lft @ rgt, M, atol=1e-6)
+        iso = lft if left else rgt.conj().T
+        np.testing.assert_allclose(iso.conj().T @ iso, np.eye(8), atol=2e-6)
