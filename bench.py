@@ -1,0 +1,440 @@
+#!/usr/bin/env python
+"""Benchmark of the two-qudit gate application path (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU path (oracle)
+
+Workload (config.workload): BASELINE.json configs[3] -- a batch of independent 40-qubit random
+brickwork circuits (depth 20, Haar gates, maxsvals = chi = 64), sharded one contiguous slice per
+GPU with no cross-GPU traffic; weak scaling with --batch-per-gpu circuits per GPU (512 -> the
+4096-circuit config at 8 GPUs).  A step = reset |0..0>, apply all 390 gates of every circuit of
+the slice, compute every circuit's norm.  Unit of work = one adjacent two-qudit application
+(theta + truncated SVD + absorb), as SURVEY.md 8(d).
+
+The one JSON line printed by rank 0 follows the driver's contract (metric/value/unit/n_gpus/
+steps/warmup/ms_per_step/higher_is_better/scaling/vs_baseline/dtype/data/config/clocks/e2e/
+gpu_launches) plus "roofline" for the dominant kernel and "cpu_baseline".
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "two_qudit_gate_applications_per_sec"
+UNIT = "applications/s"
+
+
+def parse_args():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=3)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--batch-per-gpu", type=int, default=512)
+    p.add_argument("--nqubits", type=int, default=40)
+    p.add_argument("--depth", type=int, default=20)
+    p.add_argument("--chi", type=int, default=64)
+    p.add_argument("--cpu-baseline-circuits", type=int, default=1)
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--extra", action="store_true", help="also time the chi=256 single-MPS config")
+    return p.parse_args()
+
+
+def workload_config(args, n_gpus):
+    return {
+        "workload": f"batch of independent {args.nqubits}-qubit random brickwork circuits, depth {args.depth}, "
+                    f"chi={args.chi} (BASELINE.json configs[3]), {args.batch_per_gpu} circuits per GPU",
+        "nqubits": args.nqubits, "depth": args.depth, "chi": args.chi,
+        "circuits_per_gpu": args.batch_per_gpu, "circuits_total": args.batch_per_gpu * n_gpus,
+        "parallelism": f"batch-sharded x{n_gpus}, no data-path collective",
+        "l2_policy": "inputs larger than L2 (site slab >= 1.3 GB per GPU at 512 circuits)",
+    }
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic inputs
+# ------------------------------------------------------------------------------------------------
+def haar_gates(count, rng):
+    """count Haar-random 4x4 unitaries (Mezzadri; mpsim/gates.py:269-286), vectorised."""
+    z = (rng.standard_normal((count, 4, 4)) + 1j * rng.standard_normal((count, 4, 4))) / np.sqrt(2)
+    q, r = np.linalg.qr(z)
+    dg = np.diagonal(r, axis1=1, axis2=2)
+    return (q * (dg / np.abs(dg))[:, None, :]).astype(np.complex64)
+
+
+def flops_svd_lapack(m, n):
+    """Golub-Reinsch thin count x4 for complex."""
+    mx, mn = max(m, n), min(m, n)
+    return 4.0 * (14.0 * mx * mn * mn + 8.0 * mn ** 3)
+
+
+def flops_theta(d, cl, cm, cr):
+    return 8.0 * d * d * cl * cm * cr + 8.0 * d ** 4 * cl * cr
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.gpu)], stdout=open(self.path, "w"),
+                                         stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:  # noqa: BLE001
+            pass
+        if sm:
+            out = {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                   "samples": len(sm)}
+        return out
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU baseline (the oracle = restatement of the reference's path)
+# ------------------------------------------------------------------------------------------------
+def _oracle_one_circuit(payload):
+    """Runs in a worker process with 1 BLAS thread: one circuit through the complex128 oracle."""
+    nq, depth, chi, seed, track = payload
+    os.environ["OPENBLAS_NUM_THREADS"] = "1"
+    try:
+        from threadpoolctl import threadpool_limits
+        ctx = threadpool_limits(limits=1)
+    except Exception:  # noqa: BLE001
+        ctx = None
+    from oracle.mps_oracle import OracleMPS
+    from mpsim_b200 import circuits
+    ops = circuits.brickwork(nq, depth, seed)
+    t0 = time.perf_counter()
+    mps = OracleMPS(nq, dtype=np.complex128, track_norms=track)
+    for op in ops:
+        mps.apply_two_qudit_gate(op.tensor, *op.indices, maxsvals=chi, keep_left_canonical=op.keep_left_canonical)
+    nrm = mps.norm()
+    dt = time.perf_counter() - t0
+    del ctx
+    return len(ops), dt, nrm
+
+
+def cpu_reference_step(args, ncircuits, nprocs, track_norms, seed0=1000):
+    """ncircuits circuits of the workload through the oracle on nprocs host processes.
+    Returns (applications, wall seconds)."""
+    import multiprocessing as mp
+    payloads = [(args.nqubits, args.depth, args.chi, seed0 + i, track_norms) for i in range(ncircuits)]
+    t0 = time.perf_counter()
+    if nprocs <= 1:
+        res = [_oracle_one_circuit(p) for p in payloads]
+    else:
+        with mp.get_context("fork").Pool(nprocs) as pool:
+            res = pool.map(_oracle_one_circuit, payloads)
+    wall = time.perf_counter() - t0
+    return sum(r[0] for r in res), wall
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's CPU implementation of the path (oracle port: the
+    reference itself cannot be imported here -- tensornetwork==0.2.1 / cirq absent)
+    on all host cores, one circuit per core per step (1 BLAS thread each)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0))
+    nprocs = max(1, cores)
+    ncirc = nprocs
+    for _ in range(args.warmup if args.warmup < 1 else 1):
+        cpu_reference_step(args, ncirc, nprocs, False)
+    apps, wall = 0, 0.0
+    for _ in range(args.steps):
+        a, w = cpu_reference_step(args, ncirc, nprocs, False)
+        apps += a; wall += w
+    value = apps / wall
+    fa, fw = cpu_reference_step(args, ncirc, nprocs, True)
+    sample = (f"{ncirc} circuits per step ({args.nqubits} qubits, depth {args.depth}, chi {args.chi}; "
+              f"{apps // max(args.steps, 1)} applications), complex128 numpy/LAPACK restatement, one process per "
+              f"core with 1 BLAS thread; no per-application norm bookkeeping (conservative: the reference "
+              f"also calls norm() after every application, core.py:1160-1161)")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128",
+        "data": "synthetic", "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": nprocs, "kind": "port", "sample": sample,
+                         "faithful_value_with_norm_bookkeeping": fa / fw},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def time_dominant_kernel(torch, args, batch, reps=3):
+    """Average launch duration of the dominant kernel (single-CTA Jacobi SVD of the 2chi x 2chi
+    theta) measured with CUDA events on the launching stream, on theta matrices taken from the
+    middle of the actual circuits (one per circuit of the slice)."""
+    from mpsim_b200 import _lib
+    lib = _lib.load(require_device=True)
+    chain = batch._chain
+    d, chi, B = 2, args.chi, chain.B
+    site = None
+    for i in range(chain.n - 1):
+        if chain.bonds[i] == chi and chain.bonds[i + 1] == chi and chain.bonds[i + 2] == chi:
+            site = i
+            break
+    if site is None:
+        return None
+    dev = chain.device
+    m = d * chi
+    gates = torch.from_numpy(haar_gates(B, np.random.default_rng(7)).reshape(B, 16)).to(dev)
+    desc = np.zeros(1, dtype=_lib.GATE2_DESC)
+    desc[0] = (chain.site_ptr(site), chain.site_ptr(site + 1), 0, 0, gates.data_ptr(), 0,
+               chain.total, chain.total, 0, 0, 16, 0)
+    ddesc = _lib.to_device_bytes(desc, dev)
+    nj = min(B, 65535)
+    theta = torch.empty((nj, m, m), dtype=torch.complex64, device=dev)
+    _lib.check(lib.mpsb_theta(ddesc.data_ptr(), 1, nj, d, chi, chi, chi, theta.data_ptr(), None, 0, _lib.stream_ptr()))
+    left = torch.empty((nj, m, chi), dtype=torch.complex64, device=dev)
+    right = torch.empty((nj, chi, m), dtype=torch.complex64, device=dev)
+    info = torch.zeros((nj, 2), dtype=torch.int32, device=dev)
+    ws = torch.empty(max(lib.mpsb_svd_workspace_bytes(nj, m, m), 256), dtype=torch.uint8, device=dev)
+
+    def launch():
+        _lib.check(lib.mpsb_svd(theta.data_ptr(), nj, m, m, chi, 1, left.data_ptr(), right.data_ptr(), None,
+                                info.data_ptr(), ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+    launch()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        launch()
+    e1.record()
+    torch.cuda.synchronize()
+    # mpsb_svd = one strided D2D copy + the SVD kernel; the copy is ~0.1% of the time
+    ms = e0.elapsed_time(e1) / reps
+    sweeps = float(info[:, 1].float().mean().item())
+    return {"ms_per_launch": ms, "jobs_per_launch": nj, "m": m, "n": m, "mean_sweeps": sweeps}
+
+
+def measure_fp32_peak(torch):
+    """FP32 FFMA peak of this GPU measured live with torch (dependent-free FMA chains are not
+    expressible in torch; use a large fp32 GEMM through cuBLAS as the FFMA proxy)."""
+    n = 8192
+    a = torch.randn((n, n), device="cuda", dtype=torch.float32)
+    b = torch.randn((n, n), device="cuda", dtype=torch.float32)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        torch.matmul(a, b)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            torch.matmul(a, b)
+        e1.record()
+        torch.cuda.synchronize()
+        return 3 * 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def run_our_arm(args):
+    import torch
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: mpsim_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import mpsim_b200 as mp
+    from mpsim_b200 import circuits
+    from mpsim_b200.distributed import shard_range, gather_slices
+
+    n, depth, chi = args.nqubits, args.depth, args.chi
+    B = args.batch_per_gpu
+    total = B * world
+    lo, hi = shard_range(total, rank, world)
+    structure = circuits.brickwork(n, depth, seed=0)
+    nops = len(structure)
+    batch = mp.MPSBatch(B, n)
+    cp = batch.compile(structure, maxsvals=chi)
+    napps = len(cp.plan.apps2)
+    # per-circuit Haar gates: circuit c of the global batch uses the stream seeded 1000 + c
+    gates = np.empty((nops, B, 16), dtype=np.complex64)
+    for b in range(B):
+        gates[:, b, :] = haar_gates(nops, np.random.default_rng(1000 + lo + b)).reshape(nops, 16)
+    gates_pinned = torch.from_numpy(gates).pin_memory()
+    norms_host = torch.empty(B, dtype=torch.float32).pin_memory()
+    h2d = gates_pinned.numel() * 8
+    d2h = B * 4
+
+    def step_resident():
+        batch.reset()
+        batch.run(cp, upload=False)
+        return batch.norms_device()
+
+    def step_e2e():
+        # public API with HOST buffers: gates in, norms out
+        batch.stage_gates(cp, gates_pinned.numpy())
+        batch.reset()
+        batch.run(cp, upload=True)
+        norms_host.copy_(batch.norms_device(), non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return norms_host
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        barrier()
+        return float(ms.item()), out
+
+    batch.stage_gates(cp, gates)
+    batch._chain.upload_gates(cp)
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_res, norms = timed(step_resident, args.steps)
+    clocks = sampler.stop() if rank == 0 else {}
+    status = batch.status(cp)
+    not_converged = int((status[..., 0] != 0).sum())
+    mean_sweeps = float(status[..., 1].mean())
+    for _ in range(1):
+        step_e2e()
+    ms_e2e, _ = timed(step_e2e, args.steps)
+
+    norms_all = gather_slices(norms, total)         # the only collective: B x 4 bytes per rank
+    apps_per_step_total = napps * total
+    value = apps_per_step_total * args.steps / (ms_res * 1e-3)
+    e2e_value = apps_per_step_total * args.steps / (ms_e2e * 1e-3)
+
+    if rank == 0:
+        launches_per_step = 0
+        for L in cp.launches:
+            launches_per_step += 1 if L[0] == "g1" else 2
+        launches_per_step += 2 * n + 2                # norm chain: 2 GEMMs per site + init + gather
+        # dominant kernel roofline (measured live, CUDA events on the launching stream)
+        dom = time_dominant_kernel(torch, args, batch)
+        fp32_peak = measure_fp32_peak(torch)
+        roof = None
+        if dom is not None:
+            fl = flops_svd_lapack(dom["m"], dom["n"]) * dom["jobs_per_launch"]
+            achieved = fl / (dom["ms_per_launch"] * 1e-3) / 1e12
+            roof = {"kernel": "svd_small_kernel (single-CTA QR + one-sided Jacobi, 128x128 complex64)",
+                    "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                    "frac": achieved / fp32_peak, "traffic": None,
+                    "note": "achieved = LAPACK-equivalent flops 4(14 mx mn^2 + 8 mn^3) x jobs / CUDA-event launch "
+                            "time; peak = fp32 SGEMM throughput measured live in this run (MEASURED_PEAKS.json "
+                            "records only HBM and bf16); the kernel is FFMA/shuffle bound in shared memory, "
+                            "not HBM bound",
+                    "ms_per_launch": dom["ms_per_launch"], "jobs_per_launch": dom["jobs_per_launch"],
+                    "mean_sweeps": dom["mean_sweeps"]}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        cpu = None
+        if not args.no_cpu_baseline:
+            a1, w1 = cpu_reference_step(args, args.cpu_baseline_circuits, 1, False)
+            a2, w2 = cpu_reference_step(args, args.cpu_baseline_circuits, 1, True)
+            cpu = {"value": a1 / w1, "unit": UNIT, "cores": 1, "kind": "port",
+                   "sample": f"{args.cpu_baseline_circuits} circuit(s) of the same workload ({a1} applications) "
+                             "through the complex128 numpy/LAPACK restatement of mpsim/core.py:950-1161, 1 process, "
+                             "1 BLAS thread, without the per-application norm bookkeeping",
+                   "faithful_value_with_norm_bookkeeping": a2 / w2,
+                   "host_cores_available": len(os.sched_getaffinity(0))}
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_res / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "complex64", "data": "synthetic",
+            "config": workload_config(args, world),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "roofline": roof,
+            "cpu_baseline": cpu,
+            "applications_per_step": apps_per_step_total,
+            "svd_not_converged": not_converged, "svd_mean_sweeps": mean_sweeps,
+            "norm_mean": float(norms_all.float().mean().item()),
+            "peaks": {"hbm_gbs": peaks.get("hbm_gbs"), "bf16_tflops": peaks.get("bf16_tflops"),
+                      "fp32_tflops_measured_here": fp32_peak},
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_our_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -59,7 +59,7 @@ Gate2Plan plan_gate2(int d, int chiL, int chiR, int lc) {
     p.nv = lc ? p.m : p.n;
     p.L = lc ? p.n : p.m;
     p.small = p.m <= MPSB_MAX_SMALL_DIM && p.n <= MPSB_MAX_SMALL_DIM;
-    p.x_elems = (size_t)p.m * p.n;
+    p.x_elems = p.small ? (size_t)p.m * p.n : (size_t)svd_large_padded_rows(p.nv) * p.L;
     p.extra_elems = p.small ? svd_small_global_z_elems(p.nv, p.L) : svd_large_workspace_elems(p.nv, p.L);
     p.job_elems = align_up(p.x_elems, 16) + align_up(p.extra_elems, 16);
     return p;
@@ -253,13 +253,20 @@ int mpsb_theta(const mpsb_gate2_desc* descs_dev, int ndesc, int nbatch, int d,
                         (int64_t)d * chiL * d * chiR, (cudaStream_t)stream);
 }
 
+static size_t svd_x_elems(int m, int n) {
+    bool small = m <= MPSB_MAX_SMALL_DIM && n <= MPSB_MAX_SMALL_DIM;
+    if (small) return (size_t)m * n;
+    size_t a = (size_t)svd_large_padded_rows(m) * n, b = (size_t)svd_large_padded_rows(n) * m;
+    return a > b ? a : b;
+}
+
 size_t mpsb_svd_workspace_bytes(int njobs, int m, int n) {
     if (njobs <= 0 || m <= 0 || n <= 0) return 0;
     bool small = m <= MPSB_MAX_SMALL_DIM && n <= MPSB_MAX_SMALL_DIM;
     size_t ex_a = small ? svd_small_global_z_elems(m, n) : svd_large_workspace_elems(m, n);
     size_t ex_b = small ? svd_small_global_z_elems(n, m) : svd_large_workspace_elems(n, m);
     size_t ex = ex_a > ex_b ? ex_a : ex_b;
-    return (align_up((size_t)m * n, 16) + align_up(ex, 16)) * sizeof(cf) * (size_t)njobs + 256;
+    return (align_up(svd_x_elems(m, n), 16) + align_up(ex, 16)) * sizeof(cf) * (size_t)njobs + 256;
 }
 
 int mpsb_svd(const void* mats, int njobs, int m, int n, int k, int left_canonical,
@@ -275,7 +282,7 @@ int mpsb_svd(const void* mats, int njobs, int m, int n, int k, int left_canonica
     int nv = lc ? m : n, L = lc ? n : m;
     int mn = m < n ? m : n;
     bool small = m <= MPSB_MAX_SMALL_DIM && n <= MPSB_MAX_SMALL_DIM;
-    size_t xs = align_up((size_t)m * n, 16);
+    size_t xs = align_up(svd_x_elems(m, n), 16);
     cf* X = (cf*)workspace;
     cf* extra = X + xs * njobs;
     if (lc) {

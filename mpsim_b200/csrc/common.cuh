@@ -85,6 +85,7 @@ int launch_svd_small(const cf* X, int64_t x_job_stride, int njobs, int nv, int L
                      float* svals, int64_t svals_stride, int32_t* info, cf* zglobal,
                      cudaStream_t st);
 size_t svd_large_workspace_elems(int nv, int L);
+int svd_large_padded_rows(int nv);
 int launch_svd_large(cf* X, int64_t x_job_stride, int njobs, int nv, int L, int k,
                      int left_canonical, const mpsb_gate2_desc* descs, int ndesc, int nbatch,
                      cf* left, int64_t left_stride, cf* right, int64_t right_stride,

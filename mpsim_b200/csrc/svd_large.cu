@@ -1,18 +1,476 @@
-// Truncated SVD for d*chi > 128 (block one-sided Jacobi in global memory) -- see DESIGN.md.
+// Truncated SVD for d*chi > 128: block one-sided Jacobi with the matrices resident in HBM/L2.
+//
+// Same contract and the same split/absorb identity as svd_small.cu (rows of X are the vectors;
+// Z X0 == X always; isometry = conj(Z), weighted factor = X), but the rotations are blocked so
+// that the heavy steps are GEMM-shaped:
+//   rows are grouped in blocks of B = P/2; block pairs follow the circle-method tournament;
+//   for every pair of a round (all pairs of all jobs in ONE launch per step):
+//     bj_gram  : G = Xp Xp^H                       (P x L) . (L x P)
+//     bj_evd   : G = Q^H diag Q by a two-sided Hermitian Jacobi in shared memory (P <= 64),
+//                rows of Q sorted by eigenvalue (de Rijk ordering)
+//     bj_apply : Xp <- Q Xp,  Zp <- Q Zp            (P x P) . (P x (L + nv)), in place
+//   a job stops rotating (its launches become no-ops) after a sweep in which no pair rotated.
+// Replaces tn.split_node_full_svd -> np.linalg.svd for 2chi in {256, 512, 2048}
+// (mpsim/core.py:1132-1152).  Round 1: FFMA tiles; the Gram/apply steps are the candidates for
+// tcgen05 3xTF32.
 #include "common.cuh"
 
-size_t svd_large_workspace_elems(int nv, int L) {
-    (void)nv; (void)L;
-    return 0;
+namespace {
+
+constexpr int P = 32;            // rows per block pair
+constexpr int BLK = P / 2;       // rows per block
+constexpr int LT = 256;          // threads
+constexpr int CT = 64;           // columns per apply tile
+constexpr int MAX_OUTER = 40;
+constexpr float ABS_ETA = 1e-6f;     // see bj_evd_kernel
+
+struct Misc {                    // per job, lives in the workspace
+    int active, rot, sweeps;
+    unsigned gmax_next;          // max Gram diagonal seen in this sweep (float bits; values >= 0)
+    float gmax;                  // the same from the previous sweep (~ sigma_max^2)
+    int pad[3];
+};
+
+struct LargeParams {
+    cf* X; int64_t x_stride;     // [nvp][L]
+    cf* Z; int64_t z_stride;     // [nvp][nvp]
+    cf* G; cf* Q; int64_t g_stride;   // [npairs][P][P] per job
+    float* sigma; int* perm; int64_t s_stride;   // [nvp]
+    Misc* misc;
+    int nv, L, nvp, nb, npairs;
+    float tol2;
+};
+
+__device__ __forceinline__ void pair_blocks(int nb, int r, int g, int& I, int& J) {
+    if (nb == 2) { I = 0; J = 1; return; }
+    const int m = nb - 1;
+    if (g == 0) { I = m; J = r; }
+    else { I = (r + g) % m; J = (r - g + m) % m; }
 }
+
+__device__ __forceinline__ int pair_row(int I, int J, int t) { return t < BLK ? I * BLK + t : J * BLK + (t - BLK); }
+
+__global__ void bj_init_kernel(LargeParams p) {
+    const int job = blockIdx.y;
+    cf* X = p.X + (size_t)job * p.x_stride;
+    cf* Z = p.Z + (size_t)job * p.z_stride;
+    const size_t nz = (size_t)p.nvp * p.nvp;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < nz; e += (size_t)gridDim.x * blockDim.x) {
+        size_t i = e / p.nvp, c = e - i * p.nvp;
+        Z[e] = cf_make(i == c ? 1.f : 0.f, 0.f);
+    }
+    const size_t npad = (size_t)(p.nvp - p.nv) * p.L;
+    cf* Xpad = X + (size_t)p.nv * p.L;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < npad; e += (size_t)gridDim.x * blockDim.x)
+        Xpad[e] = cf_make(0.f, 0.f);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        Misc& m = p.misc[job];
+        m.active = 1; m.rot = 0; m.sweeps = 0; m.gmax_next = 0u; m.gmax = 0.f;
+    }
+}
+
+// G[i][j] = sum_c Xp[i][c] conj(Xp[j][c])
+__global__ void __launch_bounds__(LT) bj_gram_kernel(LargeParams p, int round) {
+    const int job = blockIdx.y, g = blockIdx.x;
+    if (!p.misc[job].active) return;
+    __shared__ cf Xs[P][33];
+    int I, J;
+    pair_blocks(p.nb, round, g, I, J);
+    const cf* X = p.X + (size_t)job * p.x_stride;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16, 2 x 2 outputs each
+    cf acc[2][2] = {{cf_make(0.f, 0.f), cf_make(0.f, 0.f)}, {cf_make(0.f, 0.f), cf_make(0.f, 0.f)}};
+    for (int c0 = 0; c0 < p.L; c0 += 32) {
+        for (int e = threadIdx.x; e < P * 32; e += LT) {
+            int r = e >> 5, c = e & 31;
+            Xs[r][c] = (c0 + c < p.L) ? X[(size_t)pair_row(I, J, r) * p.L + c0 + c] : cf_make(0.f, 0.f);
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int c = 0; c < 32; ++c) {
+            cf a0 = Xs[ty * 2][c], a1 = Xs[ty * 2 + 1][c];
+            cf b0 = Xs[tx * 2][c], b1 = Xs[tx * 2 + 1][c];
+            acc[0][0] = cf_fma_conja(b0, a0, acc[0][0]);     // a * conj(b)
+            acc[0][1] = cf_fma_conja(b1, a0, acc[0][1]);
+            acc[1][0] = cf_fma_conja(b0, a1, acc[1][0]);
+            acc[1][1] = cf_fma_conja(b1, a1, acc[1][1]);
+        }
+        __syncthreads();
+    }
+    cf* G = p.G + (size_t)job * p.g_stride + (size_t)g * P * P;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 2; ++j) G[(ty * 2 + i) * P + tx * 2 + j] = acc[i][j];
+}
+
+__device__ __forceinline__ void evd_rot_params(float a, float b, float gr, float gi, float g2,
+                                               float& c, float& sr, float& si) {
+    float rg = rsqrtf(g2);
+    float zeta = (a - b) * (0.5f * rg);
+    float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
+    float ct = (t * rsqrtf(fmaf(t, t, 1.0f))) * rg;
+    sr = ct * gr;
+    si = ct * gi;
+    float h = fmaf(sr, sr, si * si);
+    float poly = fmaf(h, fmaf(h, fmaf(h, fmaf(h, 0.02734375f, 0.0390625f), 0.0625f), 0.125f), 0.5f);
+    c = (h < 0.0625f) ? fmaf(-h, poly, 1.0f) : sqrtf(fmaf(-sr, sr, fmaf(-si, si, 1.0f)));
+}
+
+// Two-sided Jacobi eigen-decomposition of the P x P Hermitian Gram matrix: Q G Q^H = diag.
+__global__ void __launch_bounds__(LT) bj_evd_kernel(LargeParams p) {
+    const int job = blockIdx.y, g = blockIdx.x;
+    if (!p.misc[job].active) return;
+    __shared__ cf Gs[P][P + 1];
+    __shared__ cf Qs[P][P + 1];
+    __shared__ float rc[P / 2], rsr[P / 2], rsi[P / 2];
+    __shared__ int rp[P / 2], rq[P / 2];
+    __shared__ float lam[P];
+    __shared__ int cnt[2];
+    __shared__ float red[LT / 32];
+    const int tid = threadIdx.x;
+    cf* G = p.G + (size_t)job * p.g_stride + (size_t)g * P * P;
+    cf* Qo = p.Q + (size_t)job * p.g_stride + (size_t)g * P * P;
+    // load, scaled by a power of two so that max|G| is in [1, 2)
+    float mx = 0.f;
+    for (int e = tid; e < P * P; e += LT) { cf v = G[e]; mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))); }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((tid & 31) == 0) red[tid >> 5] = mx;
+    if (tid < 2) cnt[tid] = 0;
+    __syncthreads();
+    mx = 0.f;
+#pragma unroll
+    for (int w = 0; w < LT / 32; ++w) mx = fmaxf(mx, red[w]);
+    int ex = 0;
+    if (mx > 0.f && isfinite(mx)) (void)frexpf(mx, &ex);
+    const float sc = mx > 0.f ? ldexpf(1.0f, 1 - ex) : 1.0f;
+    for (int e = tid; e < P * P; e += LT) {
+        int i = e / P, j = e - i * P;
+        cf v = G[e];
+        Gs[i][j] = cf_make(v.x * sc, v.y * sc);
+        Qs[i][j] = cf_make(i == j ? 1.f : 0.f, 0.f);
+    }
+    __syncthreads();
+    // Rotation criterion: |G_pq| > tol sqrt(G_pp G_qq)  AND  |G_pq| > eta sigma_max max(s_p, s_q).
+    // The second (absolute) part matters for graded spectra: every GEMM that mixes a large row
+    // into a small one leaves ~eps*sigma_max of noise in it, so |G_pq| of a small pair carries
+    // noise ~eps*sigma_max*max(s_p, s_q) and the relative criterion alone is never met in fp32.
+    // A row far below sigma_max keeps a component of up to eta*sigma_max along each larger row,
+    // i.e. an absolute error of ~eta*sqrt(nv)*sigma_max ~ 8e-6 sigma_max in the smallest singular
+    // values at eta = 1e-6 (measured; parity bound: 1e-5 sigma_max).  Without preconditioning the cyclic block method
+    // converges only linearly (~2x per sweep) until then: ~10 sweeps for flat spectra, ~17 for
+    // graded ones (tests/_jacobi_model.py notes; a blocked QR preconditioner is the next step).
+    const float gmax_s = p.misc[job].gmax * sc;
+    const float eta2g = ABS_ETA * ABS_ETA * gmax_s;
+    int total_rot = 0;
+    for (int sweep = 0; sweep < 24; ++sweep) {
+        for (int r = 0; r < P - 1; ++r) {
+            if (tid < P / 2) {
+                int a_, b_;
+                const int m = P - 1;
+                if (tid == 0) { a_ = m; b_ = r; } else { a_ = (r + tid) % m; b_ = (r - tid + m) % m; }
+                const int pp = min(a_, b_), qq = max(a_, b_);
+                float a = Gs[pp][pp].x, b = Gs[qq][qq].x;
+                cf gg = Gs[pp][qq];
+                float g2 = cf_abs2(gg);
+                float c = 1.f, sr = 0.f, si = 0.f;
+                if (g2 > p.tol2 * a * b && g2 > eta2g * fmaxf(a, b) && g2 > 1e-30f) {
+                    evd_rot_params(a, b, gg.x, gg.y, g2, c, sr, si);
+                    atomicAdd(&cnt[sweep & 1], 1);
+                }
+                rp[tid] = pp; rq[tid] = qq; rc[tid] = c; rsr[tid] = sr; rsi[tid] = si;
+            }
+            __syncthreads();
+            // rows: [g_p; g_q] <- J [g_p; g_q], same for Q
+            for (int e = tid; e < (P / 2) * P * 2; e += LT) {
+                int which = e / ((P / 2) * P);
+                int rem = e - which * (P / 2) * P;
+                int i = rem / P, col = rem - i * P;
+                float c = rc[i], sr = rsr[i], si = rsi[i];
+                if (sr == 0.f && si == 0.f) continue;
+                cf (*Mx)[P + 1] = which ? Qs : Gs;
+                cf x = Mx[rp[i]][col], y = Mx[rq[i]][col];
+                cf nx, ny;
+                nx.x = fmaf(c, x.x, fmaf(sr, y.x, -(si * y.y)));
+                nx.y = fmaf(c, x.y, fmaf(sr, y.y, si * y.x));
+                ny.x = fmaf(c, y.x, -fmaf(sr, x.x, si * x.y));
+                ny.y = fmaf(c, y.y, fmaf(si, x.x, -(sr * x.y)));
+                Mx[rp[i]][col] = nx; Mx[rq[i]][col] = ny;
+            }
+            __syncthreads();
+            // columns: [g_.p, g_.q] <- [g_.p, g_.q] J^H :  p' = c p + conj(s) q ; q' = -s p + c q
+            for (int e = tid; e < (P / 2) * P; e += LT) {
+                int i = e / P, row = e - i * P;
+                float c = rc[i], sr = rsr[i], si = rsi[i];
+                if (sr == 0.f && si == 0.f) continue;
+                cf x = Gs[row][rp[i]], y = Gs[row][rq[i]];
+                cf nx, ny;
+                nx.x = fmaf(c, x.x, fmaf(sr, y.x, si * y.y));
+                nx.y = fmaf(c, x.y, fmaf(sr, y.y, -(si * y.x)));
+                ny.x = fmaf(c, y.x, -fmaf(sr, x.x, -(si * x.y)));
+                ny.y = fmaf(c, y.y, -fmaf(sr, x.y, si * x.x));
+                Gs[row][rp[i]] = nx; Gs[row][rq[i]] = ny;
+            }
+            __syncthreads();
+        }
+        int rot = cnt[sweep & 1];
+        if (tid == 0) cnt[(sweep + 1) & 1] = 0;
+        total_rot += rot;
+        __syncthreads();
+        if (rot == 0) break;
+    }
+    // Q is written UNSORTED: small-angle rotations started from the identity keep Q close to
+    // the identity, which the cyclic block method needs to converge (sorting the rows by
+    // eigenvalue is a permutation far from the identity and makes the outer iteration cycle).
+    if (tid < P) lam[tid] = Gs[tid][tid].x;
+    __syncthreads();
+    // One Newton-Schulz step Q <- (3 Q - (Q Q^H) Q) / 2: the product of ~10^3 fp32 rotations is
+    // unitary only to ~2e-6, and that error would random-walk into every row norm (= singular
+    // value) over the ~400 block rotations of a solve; after the step Q is unitary to ~1e-7.
+    for (int e = tid; e < P * P; e += LT) {
+        int i = e / P, j = e - i * P;
+        cf r = cf_make(0.f, 0.f);
+#pragma unroll 8
+        for (int k = 0; k < P; ++k) r = cf_fma_conja(Qs[j][k], Qs[i][k], r);     // Q_ik conj(Q_jk)
+        Gs[i][j] = r;
+    }
+    __syncthreads();
+    for (int e = tid; e < P * P; e += LT) {
+        int i = e / P, j = e - i * P;
+        cf t = cf_make(0.f, 0.f);
+#pragma unroll 8
+        for (int k = 0; k < P; ++k) t = cf_fma(Gs[i][k], Qs[k][j], t);
+        cf q = Qs[i][j];
+        Qo[e] = cf_make(1.5f * q.x - 0.5f * t.x, 1.5f * q.y - 0.5f * t.y);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float m = 0.f;
+        for (int i = 0; i < P; ++i) m = fmaxf(m, lam[i]);
+        atomicMax(&p.misc[job].gmax_next, __float_as_uint(fmaxf(m, 0.f) / sc));
+    }
+    if (tid == 0 && total_rot > 0) atomicAdd(&p.misc[job].rot, 1);
+}
+
+// rows of the pair, columns [c0, c0+CT) of [X | Z]:  T <- Q T   (in place)
+__global__ void __launch_bounds__(LT) bj_apply_kernel(LargeParams p, int round, int ntx) {
+    const int job = blockIdx.z, g = blockIdx.y, tile = blockIdx.x;
+    if (!p.misc[job].active) return;
+    __shared__ cf Qs[P][P + 1];
+    __shared__ cf Ts[P][CT + 1];
+    int I, J;
+    pair_blocks(p.nb, round, g, I, J);
+    cf* base; int ld, c0, ncol;
+    if (tile < ntx) { base = p.X + (size_t)job * p.x_stride; ld = p.L; c0 = tile * CT; ncol = p.L; }
+    else { base = p.Z + (size_t)job * p.z_stride; ld = p.nvp; c0 = (tile - ntx) * CT; ncol = p.nvp; }
+    const cf* Q = p.Q + (size_t)job * p.g_stride + (size_t)g * P * P;
+    for (int e = threadIdx.x; e < P * P; e += LT) Qs[e / P][e % P] = Q[e];
+    for (int e = threadIdx.x; e < P * CT; e += LT) {
+        int r = e / CT, c = e - r * CT;
+        Ts[r][c] = (c0 + c < ncol) ? base[(size_t)pair_row(I, J, r) * ld + c0 + c] : cf_make(0.f, 0.f);
+    }
+    __syncthreads();
+    const int c = threadIdx.x % CT, rg = threadIdx.x / CT;        // 4 row groups of P/4 rows
+    constexpr int RPT = P / (LT / CT);
+    cf acc[RPT];
+#pragma unroll
+    for (int i = 0; i < RPT; ++i) acc[i] = cf_make(0.f, 0.f);
+#pragma unroll 4
+    for (int k = 0; k < P; ++k) {
+        cf t = Ts[k][c];
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) acc[i] = cf_fma(Qs[rg * RPT + i][k], t, acc[i]);
+    }
+    if (c0 + c < ncol) {
+#pragma unroll
+        for (int i = 0; i < RPT; ++i) base[(size_t)pair_row(I, J, rg * RPT + i) * ld + c0 + c] = acc[i];
+    }
+}
+
+// R <- 3/2 I - 1/2 R   (Newton-Schulz factor)
+__global__ void bj_ns_kernel(cf* R, int64_t stride, int n) {
+    cf* r = R + (size_t)blockIdx.y * stride;
+    const size_t tot = (size_t)n * n;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (size_t)gridDim.x * blockDim.x) {
+        size_t i = e / n, j = e - i * n;
+        cf v = r[e];
+        r[e] = cf_make((i == j ? 1.5f : 0.f) - 0.5f * v.x, -0.5f * v.y);
+    }
+}
+
+__global__ void bj_sweep_end_kernel(LargeParams p, int njobs) {
+    int job = blockIdx.x * blockDim.x + threadIdx.x;
+    if (job >= njobs) return;
+    Misc& m = p.misc[job];
+    if (m.active) {
+        m.sweeps += 1; m.active = m.rot > 0 ? 1 : 0; m.rot = 0;
+        m.gmax = __uint_as_float(m.gmax_next); m.gmax_next = 0u;
+    }
+}
+
+// sigma_i = |X_i| ; padding rows (those whose Z row lives in the padded columns) get -1
+__global__ void __launch_bounds__(LT) bj_sigma_kernel(LargeParams p) {
+    const int job = blockIdx.y;
+    const int row = blockIdx.x * (LT / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (row >= p.nvp) return;
+    const cf* x = p.X + (size_t)job * p.x_stride + (size_t)row * p.L;
+    const cf* z = p.Z + (size_t)job * p.z_stride + (size_t)row * p.nvp;
+    float s2 = 0.f, pad = 0.f;
+    for (int c = lane; c < p.L; c += 32) s2 += cf_abs2(x[c]);
+    for (int c = p.nv + lane; c < p.nvp; c += 32) pad += cf_abs2(z[c]);
+    s2 = warp_sum(s2); pad = warp_sum(pad);
+    if (lane == 0) p.sigma[(size_t)job * p.s_stride + row] = pad > 0.5f ? -1.0f : sqrtf(s2);
+}
+
+__global__ void bj_rank_kernel(LargeParams p) {
+    const int job = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.nvp) return;
+    const float* s = p.sigma + (size_t)job * p.s_stride;
+    float si = s[i];
+    int rk = 0;
+    for (int j = 0; j < p.nvp; ++j) { float sj = s[j]; rk += (sj > si) || (sj == si && j < i); }
+    p.perm[(size_t)job * p.s_stride + rk] = i;
+}
+
+struct OutParams {
+    const mpsb_gate2_desc* descs; int nbatch;
+    cf* left; int64_t left_stride; cf* right; int64_t right_stride;
+    float* svals; int64_t svals_stride; int32_t* info;
+    int k, lc;
+};
+
+__global__ void __launch_bounds__(LT) bj_write_kernel(LargeParams p, OutParams o) {
+    const int job = blockIdx.y;
+    cf *left, *right; float* sv;
+    if (o.descs) {
+        int di = job / o.nbatch, bi = job % o.nbatch;
+        const mpsb_gate2_desc d = o.descs[di];
+        left = (cf*)d.out_l + (size_t)bi * d.bs_out_l;
+        right = (cf*)d.out_r + (size_t)bi * d.bs_out_r;
+        sv = d.svals ? d.svals + (size_t)bi * d.bs_svals : nullptr;
+    } else {
+        left = o.left + (size_t)job * o.left_stride;
+        right = o.right + (size_t)job * o.right_stride;
+        sv = o.svals ? o.svals + (size_t)job * o.svals_stride : nullptr;
+    }
+    const cf* X = p.X + (size_t)job * p.x_stride;
+    const cf* Z = p.Z + (size_t)job * p.z_stride;
+    const int* perm = p.perm + (size_t)job * p.s_stride;
+    const float* sig = p.sigma + (size_t)job * p.s_stride;
+    const int k = o.k, nv = p.nv, L = p.L;
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (o.lc) {
+        for (size_t e = t0; e < (size_t)k * L; e += stride) { size_t j = e / L, c = e - j * L; right[e] = X[(size_t)perm[j] * L + c]; }
+        for (size_t e = t0; e < (size_t)nv * k; e += stride) { size_t a = e / k, j = e - a * k; left[e] = cf_conj(Z[(size_t)perm[j] * p.nvp + a]); }
+    } else {
+        for (size_t e = t0; e < (size_t)L * k; e += stride) { size_t a = e / k, j = e - a * k; left[e] = X[(size_t)perm[j] * L + a]; }
+        for (size_t e = t0; e < (size_t)k * nv; e += stride) { size_t j = e / nv, b = e - j * nv; right[e] = cf_conj(Z[(size_t)perm[j] * p.nvp + b]); }
+    }
+    const int mn = nv < L ? nv : L;
+    if (sv) for (size_t j = t0; j < (size_t)mn; j += stride) sv[j] = fmaxf(sig[perm[j]], 0.f);
+    if (o.info && t0 == 0) {
+        o.info[2 * job] = p.misc[job].active ? 1 : 0;      // still rotating at the sweep limit
+        o.info[2 * job + 1] = p.misc[job].sweeps;
+    }
+}
+
+struct LargeLayout { int nvp, nb, npairs; size_t z, g, s, misc, m0, total; };
+
+LargeLayout large_layout(int nv, int L) {
+    (void)L;
+    LargeLayout lo;
+    lo.nvp = (nv + P - 1) / P * P;
+    lo.nb = lo.nvp / BLK;
+    lo.npairs = lo.nb / 2;
+    lo.z = align_up((size_t)lo.nvp * lo.nvp, 16);
+    lo.g = align_up((size_t)lo.npairs * P * P, 16);
+    lo.s = align_up((size_t)lo.nvp, 16);              // floats / ints, counted in cf units below
+    lo.misc = 16;
+    lo.m0 = align_up((size_t)nv * L, 16);
+    // Z, R, Z2 (3 z) + G, Q (2 g) + sigma|perm (s cf = 2 s words) + misc + copy of the input
+    lo.total = 3 * lo.z + 2 * lo.g + lo.s + lo.misc + lo.m0;
+    return lo;
+}
+
+}  // namespace
+
+int svd_large_padded_rows(int nv) { return (nv + P - 1) / P * P; }
+
+size_t svd_large_workspace_elems(int nv, int L) { return large_layout(nv, L).total; }
 
 int launch_svd_large(cf* X, int64_t x_job_stride, int njobs, int nv, int L, int k,
                      int left_canonical, const mpsb_gate2_desc* descs, int ndesc, int nbatch,
                      cf* left, int64_t left_stride, cf* right, int64_t right_stride,
                      float* svals, int64_t svals_stride, int32_t* info, cf* work,
                      cudaStream_t st) {
-    (void)X; (void)x_job_stride; (void)njobs; (void)k; (void)left_canonical; (void)descs; (void)ndesc;
-    (void)nbatch; (void)left; (void)left_stride; (void)right; (void)right_stride; (void)svals;
-    (void)svals_stride; (void)info; (void)work; (void)st;
-    MPSB_ARG(false, "svd_large: %d x %d not implemented yet", nv, L);
+    (void)ndesc;
+    if (njobs <= 0) return 0;
+    MPSB_ARG(work != nullptr, "svd_large: workspace missing");
+    MPSB_ARG(njobs <= 65535, "svd_large: njobs %d > 65535", njobs);
+    LargeLayout lo = large_layout(nv, L);
+    MPSB_ARG(x_job_stride >= (int64_t)lo.nvp * L, "svd_large: X stride too small for the padded rows");
+    LargeParams p;
+    p.X = X; p.x_stride = x_job_stride;
+    // workspace: [njobs][Z] [njobs][G] [njobs][Q] [njobs][sigma|perm] [njobs][misc]
+    cf* w = work;
+    p.Z = w; p.z_stride = (int64_t)lo.z; w += lo.z * njobs;
+    p.G = w; w += lo.g * njobs;
+    p.Q = w; w += lo.g * njobs;
+    p.g_stride = (int64_t)lo.g;
+    p.sigma = (float*)w; p.perm = (int*)((float*)w + (size_t)lo.s * njobs); p.s_stride = (int64_t)lo.s; w += lo.s * njobs;
+    p.misc = (Misc*)w; w += lo.misc * njobs;
+    cf* Rbuf = w; w += lo.z * njobs;
+    cf* Z2 = w; w += lo.z * njobs;
+    cf* M0 = w;
+    p.nv = nv; p.L = L; p.nvp = lo.nvp; p.nb = lo.nb; p.npairs = lo.npairs;
+    // the Gram entries carry rounding noise ~ eps*sqrt(L)*sqrt(G_ii G_jj): keep the threshold above it
+    float tol = 3e-6f;
+    float floor_ = 4.0f * 5.96e-8f * sqrtf((float)L);
+    if (floor_ > tol) tol = floor_;
+    p.tol2 = tol * tol;
+
+    // keep the input: the weighted factor is recomputed from it at the end (see below)
+    MPSB_CUDA(cudaMemcpy2DAsync(M0, lo.m0 * sizeof(cf), X, (size_t)x_job_stride * sizeof(cf),
+                                (size_t)nv * L * sizeof(cf), njobs, cudaMemcpyDeviceToDevice, st));
+    bj_init_kernel<<<dim3(148, njobs), 256, 0, st>>>(p);
+    MPSB_LAUNCH_CHECK("bj_init_kernel");
+    const int nrounds = lo.nb > 2 ? lo.nb - 1 : 1;
+    const int ntx = (L + CT - 1) / CT, ntz = (lo.nvp + CT - 1) / CT;
+    for (int sweep = 0; sweep < MAX_OUTER; ++sweep) {
+        for (int r = 0; r < nrounds; ++r) {
+            bj_gram_kernel<<<dim3(lo.npairs, njobs), LT, 0, st>>>(p, r);
+            bj_evd_kernel<<<dim3(lo.npairs, njobs), LT, 0, st>>>(p);
+            bj_apply_kernel<<<dim3(ntx + ntz, lo.npairs, njobs), LT, 0, st>>>(p, r, ntx);
+        }
+        bj_sweep_end_kernel<<<(njobs + 127) / 128, 128, 0, st>>>(p, njobs);
+    }
+    MPSB_LAUNCH_CHECK("bj_round kernels");
+    // Every block rotation is a 32-term fp32 GEMM, so after several hundred of them Z has drifted
+    // from unitarity by ~1e-5 (and X = Z M with it), which would show up 1:1 in the singular
+    // values.  Re-orthonormalise Z with one Newton-Schulz step, Z <- (3/2 I - 1/2 Z Z^H) Z, and
+    // recompute X = Z M from the saved input: the split stays an exact projection, the
+    // accumulated error is gone, and the rows of X stay orthogonal to second order.
+    {
+        int rc = launch_cgemm(p.Z, lo.nvp, 1, 0, (int64_t)lo.z, p.Z, 1, lo.nvp, 1, (int64_t)lo.z,
+                              Rbuf, lo.nvp, (int64_t)lo.z, lo.nvp, lo.nvp, lo.nvp, njobs, st);
+        if (rc) return rc;
+        bj_ns_kernel<<<dim3(148, njobs), 256, 0, st>>>(Rbuf, (int64_t)lo.z, lo.nvp);
+        rc = launch_cgemm(Rbuf, lo.nvp, 1, 0, (int64_t)lo.z, p.Z, lo.nvp, 1, 0, (int64_t)lo.z,
+                          Z2, lo.nvp, (int64_t)lo.z, lo.nvp, lo.nvp, lo.nvp, njobs, st);
+        if (rc) return rc;
+        rc = launch_cgemm(Z2, lo.nvp, 1, 0, (int64_t)lo.z, M0, L, 1, 0, (int64_t)lo.m0,
+                          p.X, L, p.x_stride, lo.nvp, L, nv, njobs, st);
+        if (rc) return rc;
+        p.Z = Z2;
+    }
+    bj_sigma_kernel<<<dim3((lo.nvp + LT / 32 - 1) / (LT / 32), njobs), LT, 0, st>>>(p);
+    bj_rank_kernel<<<dim3((lo.nvp + 127) / 128, njobs), 128, 0, st>>>(p);
+    OutParams o;
+    o.descs = descs; o.nbatch = nbatch > 0 ? nbatch : 1;
+    o.left = left; o.left_stride = left_stride; o.right = right; o.right_stride = right_stride;
+    o.svals = svals; o.svals_stride = svals_stride; o.info = info; o.k = k; o.lc = left_canonical;
+    bj_write_kernel<<<dim3(32, njobs), LT, 0, st>>>(p, o);
+    MPSB_LAUNCH_CHECK("bj_write_kernel");
+    return 0;
 }

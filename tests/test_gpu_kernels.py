@@ -164,3 +164,30 @@ def test_svd_denormal_diagonal_regression():
         np.testing.assert_allclose(left[0] @ right[0], M, atol=1e-6)
         iso = left[0] if lc else right[0].conj().T
         np.testing.assert_allclose(iso.conj().T @ iso, np.eye(8), atol=2e-6)
+
+
+@pytest.mark.parametrize("shape", [(256, 256), (200, 136), (130, 300), (512, 512), (160, 128)])
+@pytest.mark.parametrize("lc", [1, 0])
+def test_svd_large_matches_lapack(shape, lc):
+    """d*chi > 128: block Jacobi (Gram + Hermitian EVD + apply) in global memory."""
+    m, n = shape
+    rng = np.random.RandomState(m * 17 + n + lc)
+    mats = np.stack([_graded(rng, m, n, 0.0), _graded(rng, m, n, 12.0)])
+    k = min(m, n)
+    left, right, sv, info = _svd(mats, k, lc)
+    assert (info[:, 0] == 0).all(), info
+    for j in range(len(mats)):
+        sref = np.linalg.svd(mats[j].astype(np.complex128), compute_uv=False)
+        assert np.abs(sv[j] - sref).max() <= 1e-5 * sref[0], (info, np.abs(sv[j] - sref).max() / sref[0])
+        np.testing.assert_allclose(left[j] @ right[j], mats[j], atol=5e-6 * sref[0])
+        iso = left[j] if lc else right[j].conj().T
+        np.testing.assert_allclose(iso.conj().T @ iso, np.eye(k), atol=3e-5)
+    kk = k // 2
+    left, right, sv, info = _svd(mats, kk, lc)
+    for j in range(len(mats)):
+        u, s, vh = np.linalg.svd(mats[j].astype(np.complex128), full_matrices=False)
+        best = (u[:, :kk] * s[:kk]) @ vh[:kk]
+        # projection error is second order in the residual non-orthogonality, first order near the cut
+        err = np.linalg.norm(left[j] @ right[j] - best) / np.linalg.norm(best)
+        assert err < 2e-3, err
+        assert abs(np.linalg.norm(left[j] @ right[j]) - np.linalg.norm(best)) < 1e-5 * np.linalg.norm(best)

@@ -237,7 +237,8 @@ def test_apply_with_operations_and_dispatcher():            # core_test.py:1187-
 
 
 # ---- against the complex128 oracle on seeded random circuits -------------------------------------
-@pytest.mark.parametrize("n,depth,chi,seed", [(8, 8, None, 1), (12, 10, 8, 2), (16, 12, 16, 3), (20, 10, 64, 1)])
+@pytest.mark.parametrize("n,depth,chi,seed", [(8, 8, None, 1), (12, 10, 8, 2), (16, 12, 16, 3), (20, 10, 64, 1),
+                                               (16, 14, 96, 4)])   # last: d*chi = 192 > 128, large-chi path
 def test_brickwork_vs_oracle(n, depth, chi, seed):
     import mpsim_b200 as mp
     from mpsim_b200 import circuits
@@ -253,10 +254,14 @@ def test_brickwork_vs_oracle(n, depth, chi, seed):
         mps.apply_two_qudit_gate(mp.Node(op.tensor), *op.indices, keep_left_canonical=op.keep_left_canonical, **kw)
         svs += mps.last_singular_values()
     assert mps.bond_dimensions() == ora.bond_dimensions()
+    # free-running comparison: per-application errors compound over the depth of the circuit.
+    # The single-CTA path (d*chi <= 128) holds 1e-5 even so; the block-Jacobi path (d*chi > 128)
+    # meets 1e-5 per application (teacher-forced, tests/test_gpu_kernels.py) and 5e-5 free-running.
+    sv_tol = SV_TOL if (chi is None or 2 * chi <= 128) else 5 * SV_TOL
     for s, t in zip(svs, ora.trace):
         assert s["k"] == t["k"]
         ref = np.concatenate([t["s_kept"], t["s_trunc"]])
-        assert np.abs(s["svals"] - ref).max() <= SV_TOL * ref.max()
+        assert np.abs(s["svals"] - ref).max() <= sv_tol * ref.max()
     assert abs(mps.norm() - ora.norm()) < 1e-4
     wf, wref = mps.wavefunction(), ora.wavefunction()
     np.testing.assert_allclose(wf, wref, atol=AMP_TOL)
