@@ -11,9 +11,11 @@
 //      ~9 sweeps independently of how graded the spectrum is (plain Jacobi on X needs 15-25).
 //   2. One-sided Jacobi on the rows of Y, the same 2x2 unitaries accumulated into Z, so that
 //      Z X0 == Y always.  Rows are visited by a block tournament: 4-row blocks are paired by the
-//      circle method; a warp owns a pair of blocks, keeps its 8 rows of Y and Z in registers
-//      (lane owns elements lane, lane+32, ...) and performs the 16 cross rotations (plus the 12
-//      intra-block ones in the first round of a sweep) with warp-shuffle reductions.
+//      circle method; a warp owns a pair of blocks, keeps its 8 rows of Y in registers
+//      (lane owns elements lane, lane+32, ...), performs the 16 cross rotations (plus the 12
+//      intra-block ones in the first round of a sweep) with warp-shuffle reductions, logs them
+//      to shared memory and replays them on its 8 rows of Z in the same registers (two phases
+//      keep the kernel under 128 registers, so 16 warps are resident instead of 8).
 //   3. sigma_j = |Y_j|, stable descending rank sort (ties keep the lower index: this is what
 //      reproduces the reference on Bell + maxsvals=1, README.md:48-53), keep the first k.
 //   4. Split/absorb without any division: the isometry is conj(Z) (a product of unitaries, so
@@ -26,9 +28,10 @@
 
 namespace {
 
-constexpr int ST = 256;          // threads per CTA
-constexpr int NW = ST / 32;      // warps
+constexpr int ST = 512;          // threads per CTA
+constexpr int NW = ST / 32;      // warps: one 8-row group each at nv = 128
 constexpr int EPL = 4;           // elements per lane per row (row length <= 128)
+constexpr int NSLOT = 28;        // rotations per group step: 12 intra-block + 16 cross
 
 struct SvdSmallParams {
     const cf* X; int64_t x_stride;
@@ -43,11 +46,11 @@ struct SvdSmallParams {
     int max_sweeps; float tol2; int do_qr;
 };
 
+// (c, s, t|g|) of [[c, s], [-conj(s), c]] diagonalising [[a, g], [conj(g), b]]; s first, then
+// c = sqrt(1 - |s|^2) derived from s (series near 1) so the rotation is unitary to rounding
+// WITHOUT bias -- see tests/_jacobi_model.py:rotation_params.
 __device__ __forceinline__ void rot_params(float a, float b, float gr, float gi, float g2,
                                            float& c, float& sr, float& si, float& tg) {
-    // (c, s) of [[c, s], [-conj(s), c]] diagonalising [[a, g], [conj(g), b]]; s first, then
-    // c = sqrt(1 - |s|^2) derived from s (series near 1) so the rotation is unitary to rounding
-    // WITHOUT bias -- see tests/_jacobi_model.py:rotation_params.
     float rg = rsqrtf(g2);
     float zeta = (a - b) * (0.5f * rg);
     float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
@@ -72,13 +75,17 @@ __device__ __forceinline__ void rot_apply(float c, float sr, float si, cf& p, cf
     q = nq_;
 }
 
-// One sub-round: NP disjoint pairs (PA[i], PB[i]) of the warp's 8 rows.
-template <int NP>
-__device__ __forceinline__ int sub_round(cf (&y)[8][EPL], cf (&z)[8][EPL], float (&a)[8],
-                                         const int (&PA)[NP], const int (&PB)[NP], float tol2) {
-    float gr[NP], gi[NP];
+// One sub-round on the Y rows of a group: 4 disjoint pairs (A_i, B_i).  The four Gram entries are
+// reduced together; lane l then computes the rotation of pair (l & 3) only and the parameters
+// are exchanged by shuffles (4x fewer scalar instructions than every lane doing all four).
+// The rotations are logged to rot[slot..slot+3] = (c, s.re, s.im, rotated?) for the Z phase.
+template <int A0, int A1, int A2, int A3, int B0, int B1, int B2, int B3>
+__device__ __forceinline__ int sub_round_y(cf (&y)[8][EPL], float (&a)[8], float tol2,
+                                           float4* rot, int slot, int lane) {
+    constexpr int PA[4] = {A0, A1, A2, A3}, PB[4] = {B0, B1, B2, B3};
+    float gr[4], gi[4];
 #pragma unroll
-    for (int i = 0; i < NP; ++i) {
+    for (int i = 0; i < 4; ++i) {
         float r = 0.f, m = 0.f;
 #pragma unroll
         for (int t = 0; t < EPL; ++t) {
@@ -91,30 +98,53 @@ __device__ __forceinline__ int sub_round(cf (&y)[8][EPL], cf (&z)[8][EPL], float
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-        for (int i = 0; i < NP; ++i) {
+        for (int i = 0; i < 4; ++i) {
             gr[i] += __shfl_xor_sync(0xffffffffu, gr[i], o);
             gi[i] += __shfl_xor_sync(0xffffffffu, gi[i], o);
         }
     }
-    int nrot = 0;
+    // this lane's pair
+    const int sel = lane & 3;
+    float mgr = gr[0], mgi = gi[0], ap = a[PA[0]], aq = a[PB[0]];
 #pragma unroll
-    for (int i = 0; i < NP; ++i) {
-        float g2 = fmaf(gr[i], gr[i], gi[i] * gi[i]);
-        float ap = a[PA[i]], aq = a[PB[i]];
-        if (g2 > tol2 * ap * aq && g2 > 1e-30f) {      // warp-uniform (all lanes hold the sums)
-            float c, sr, si, tg;
-            rot_params(ap, aq, gr[i], gi[i], g2, c, sr, si, tg);
+    for (int i = 1; i < 4; ++i) {
+        if (sel == i) { mgr = gr[i]; mgi = gi[i]; ap = a[PA[i]]; aq = a[PB[i]]; }
+    }
+    const float g2 = fmaf(mgr, mgr, mgi * mgi);
+    float c = 1.f, sr = 0.f, si = 0.f, tg = 0.f;
+    const bool dorot = (g2 > tol2 * ap * aq) && (g2 > 1e-30f);
+    if (dorot) rot_params(ap, aq, mgr, mgi, g2, c, sr, si, tg);
+    if (lane < 4) rot[slot + lane] = make_float4(c, sr, si, dorot ? 1.f : 0.f);
+    const unsigned flags = __ballot_sync(0xffffffffu, dorot) & 0xFu;
+    if (flags == 0u) return 0;
 #pragma unroll
-            for (int t = 0; t < EPL; ++t) {
-                rot_apply(c, sr, si, y[PA[i]][t], y[PB[i]][t]);
-                rot_apply(c, sr, si, z[PA[i]][t], z[PB[i]][t]);
-            }
-            a[PA[i]] = fmaxf(ap + tg, 0.f);
-            a[PB[i]] = fmaxf(aq - tg, 0.f);
-            ++nrot;
+    for (int i = 0; i < 4; ++i) {
+        if (flags & (1u << i)) {                       // warp-uniform
+            const float ci = __shfl_sync(0xffffffffu, c, i);
+            const float sri = __shfl_sync(0xffffffffu, sr, i);
+            const float sii = __shfl_sync(0xffffffffu, si, i);
+            const float tgi = __shfl_sync(0xffffffffu, tg, i);
+#pragma unroll
+            for (int t = 0; t < EPL; ++t) rot_apply(ci, sri, sii, y[PA[i]][t], y[PB[i]][t]);
+            a[PA[i]] = fmaxf(a[PA[i]] + tgi, 0.f);
+            a[PB[i]] = fmaxf(a[PB[i]] - tgi, 0.f);
         }
     }
-    return nrot;
+    return __popc(flags);
+}
+
+// The same sub-round replayed on the Z rows from the logged rotations.
+template <int A0, int A1, int A2, int A3, int B0, int B1, int B2, int B3>
+__device__ __forceinline__ void sub_round_z(cf (&z)[8][EPL], const float4* rot, int slot) {
+    constexpr int PA[4] = {A0, A1, A2, A3}, PB[4] = {B0, B1, B2, B3};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float4 r = rot[slot + i];                // broadcast load
+        if (r.w != 0.f) {
+#pragma unroll
+            for (int t = 0; t < EPL; ++t) rot_apply(r.x, r.y, r.z, z[PA[i]][t], z[PB[i]][t]);
+        }
+    }
 }
 
 __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
@@ -123,13 +153,14 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nv = P.nv, L = P.L, nvp = P.nvp, LS = P.LS, ZS = P.ZS;
 
-    cf* Ys = (cf*)smem_raw;                        // [nvp][LS]
+    float4* rotbuf = smem_raw;                     // [NW][NSLOT] (16-byte aligned first)
+    cf* Ys = (cf*)(rotbuf + NW * NSLOT);           // [nvp][LS]
     cf* Zs = Ys + (size_t)nvp * LS;                // [nz_smem][ZS]
     cf* vbuf = Zs + (size_t)P.nz_smem * ZS;        // [2][nvp]
     float* sig = (float*)(vbuf + 2 * nvp);         // [nvp]
     int* perm = (int*)(sig + nvp);                 // [nvp]
-    float* scal = (float*)(perm + nvp);            // [8]
-    int* cnt = (int*)(scal + 8);                   // [2]
+    float* scal = (float*)(perm + nvp);            // [NW] (also the QR scalars: 8 used)
+    int* cnt = (int*)(scal + NW);                  // [2]
     cf* zg = P.zg + (size_t)job * P.zg_stride;
     const int nzs = P.nz_smem;
     auto zrow = [&](int i) -> cf* { return i < nzs ? Zs + (size_t)i * ZS : zg + (size_t)(i - nzs) * ZS; };
@@ -158,14 +189,14 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
         if (i < nv && c < L) { v = X[(size_t)i * L + c]; v.x *= scale_in; v.y *= scale_in; }
         Ys[e] = v;
     }
-    for (int i = 0; i < nv; ++i) {
-        cf* zr = zrow(i);
-        for (int c = tid; c < ZS; c += ST) zr[c] = cf_make(c == i ? 1.f : 0.f, 0.f);
+    for (int e = tid; e < nv * ZS; e += ST) {
+        int i = e / ZS, c = e - i * ZS;
+        zrow(i)[c] = cf_make(c == i ? 1.f : 0.f, 0.f);
     }
     if (tid < 2) cnt[tid] = 0;
     __syncthreads();
 
-    // ---- phase 1: Householder QR, one thread per column of [Y | Z] ---------------------------
+    // ---- phase 1: Householder QR, two threads per column of [Y | Z] (rows split even/odd) ----
     const int J = P.do_qr ? min(nv - 1, L) : 0;
     if (J > 0) {
         if (warp == 0) {
@@ -179,9 +210,10 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
             if (lane == 0) { cf x0 = Ys[0]; scal[0] = x0.x; scal[1] = x0.y; scal[2] = t2; }
         }
         __syncthreads();
-        const bool isY = tid < L;
-        const bool isZ = !isY && (tid - L) < nv;
-        const int col = isY ? tid : tid - L;
+        const int colid = tid >> 1, half = tid & 1;
+        const bool isY = colid < L;
+        const bool isZ = !isY && (colid - L) < nv;
+        const int col = isY ? colid : colid - L;
         for (int j = 0; j < J; ++j) {
             const int cur = j & 1, nxt = cur ^ 1;
             const cf* vb = vbuf + cur * nvp;
@@ -196,59 +228,56 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
             if (ax0sq < 1e-30f) { x0 = cf_make(0.f, 0.f); ax0sq = 0.f; }
             // skip the reflector when the column is already reduced, or so small that
             // 1/|x|^2 would overflow (QR is only a preconditioner: any unitary Z is valid)
-            if (tail2 > 0.f && tail2 + ax0sq > 1e-30f) {
+            const bool reflect = tail2 > 0.f && tail2 + ax0sq > 1e-30f;
+            cf v0 = cf_make(0.f, 0.f), alpha = cf_make(0.f, 0.f);
+            float tau = 0.f;
+            if (reflect) {
                 float ax0 = sqrtf(ax0sq);
                 float normx = sqrtf(tail2 + ax0sq);
                 cf ph = ax0 > 0.f ? cf_scale(1.0f / ax0, x0) : cf_make(1.f, 0.f);
-                cf alpha = cf_scale(-normx, ph);
-                cf v0 = cf_sub(x0, alpha);
-                float tau = 1.0f / (normx * (normx + ax0));
-                if (isY && col == j) {
-                    Ys[(size_t)j * LS + j] = alpha;
-                    for (int i = j + 1; i < nv; ++i) Ys[(size_t)i * LS + j] = cf_make(0.f, 0.f);
-                } else if ((isY && col > j) || isZ) {
-                    cf w;
-                    if (isY) {
-                        w = cf_fma_conja(v0, Ys[(size_t)j * LS + col], cf_make(0.f, 0.f));
-                        for (int i = j + 1; i < nv; ++i) w = cf_fma_conja(vb[i], Ys[(size_t)i * LS + col], w);
-                    } else {
-                        w = cf_fma_conja(v0, zrow(j)[col], cf_make(0.f, 0.f));
-                        for (int i = j + 1; i < nv; ++i) w = cf_fma_conja(vb[i], zrow(i)[col], w);
-                    }
-                    cf tw = cf_scale(-tau, w);
-                    float t2 = 0.f;
-                    if (isY) {
-                        cf* pj = &Ys[(size_t)j * LS + col];
-                        *pj = cf_fma(v0, tw, *pj);
-                        for (int i = j + 1; i < nv; ++i) {
-                            cf* pi = &Ys[(size_t)i * LS + col];
-                            cf nvl = cf_fma(vb[i], tw, *pi);
-                            *pi = nvl;
-                            if (record) { vn[i] = nvl; if (i > j + 1) t2 += cf_abs2(nvl); }
-                        }
-                    } else {
-                        cf* pj = &zrow(j)[col];
-                        *pj = cf_fma(v0, tw, *pj);
-                        for (int i = j + 1; i < nv; ++i) {
-                            cf* pi = &zrow(i)[col];
-                            *pi = cf_fma(vb[i], tw, *pi);
-                        }
-                    }
-                    if (record) {
-                        cf x0n = Ys[(size_t)(j + 1) * LS + col];
-                        scal[nxt * 4 + 0] = x0n.x; scal[nxt * 4 + 1] = x0n.y; scal[nxt * 4 + 2] = t2;
+                alpha = cf_scale(-normx, ph);
+                v0 = cf_sub(x0, alpha);
+                tau = 1.0f / (normx * (normx + ax0));
+            }
+            const bool upd = reflect && ((isY && col > j) || isZ);
+            // pass 1: w = v^H A[:, col] over this thread's rows (j + half, j + half + 2, ...)
+            cf w = cf_make(0.f, 0.f);
+            if (upd) {
+                for (int i = j + half; i < nv; i += 2) {
+                    cf vi = (i == j) ? v0 : vb[i];
+                    cf aij = isY ? Ys[(size_t)i * LS + col] : zrow(i)[col];
+                    w = cf_fma_conja(vi, aij, w);
+                }
+            }
+            w.x += __shfl_xor_sync(0xffffffffu, w.x, 1);
+            w.y += __shfl_xor_sync(0xffffffffu, w.y, 1);
+            // pass 2: A[:, col] -= tau v w ; the owner of column j+1 records the next reflector
+            float t2 = 0.f;
+            if (upd) {
+                cf tw = cf_scale(-tau, w);
+                for (int i = j + half; i < nv; i += 2) {
+                    cf vi = (i == j) ? v0 : vb[i];
+                    cf* pa = isY ? &Ys[(size_t)i * LS + col] : &zrow(i)[col];
+                    cf nvl = cf_fma(vi, tw, *pa);
+                    *pa = nvl;
+                    if (record && i > j) {
+                        vn[i] = nvl;
+                        if (i > j + 1) t2 += cf_abs2(nvl);
+                        else { scal[nxt * 4 + 0] = nvl.x; scal[nxt * 4 + 1] = nvl.y; }
                     }
                 }
-            } else if (record) {     // reflector skipped (column already reduced): H = I
-                float t2 = 0.f;
-                for (int i = j + 1; i < nv; ++i) {
+            } else if (reflect && isY && col == j) {
+                for (int i = j + half; i < nv; i += 2) Ys[(size_t)i * LS + j] = (i == j) ? alpha : cf_make(0.f, 0.f);
+            } else if (!reflect && record) {
+                for (int i = j + 1 + half; i < nv; i += 2) {
                     cf v = Ys[(size_t)i * LS + col];
                     vn[i] = v;
                     if (i > j + 1) t2 += cf_abs2(v);
+                    else { scal[nxt * 4 + 0] = v.x; scal[nxt * 4 + 1] = v.y; }
                 }
-                cf x0n = Ys[(size_t)(j + 1) * LS + col];
-                scal[nxt * 4 + 0] = x0n.x; scal[nxt * 4 + 1] = x0n.y; scal[nxt * 4 + 2] = t2;
             }
+            t2 += __shfl_xor_sync(0xffffffffu, t2, 1);
+            if (record && half == 0) scal[nxt * 4 + 2] = t2;
             __syncthreads();
         }
     }
@@ -260,6 +289,7 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
     const int ngroups = nb / 2;
     const int nrounds = nb > 2 ? nb - 1 : 1;
     const int ylanes = P.LC / 32, zlanes = P.ZC / 32;
+    float4* rot = rotbuf + warp * NSLOT;
     int sweeps = 0, status = 0;
     if (nact >= 2) {
         status = 1;
@@ -274,19 +304,16 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
                     int rows[8];
 #pragma unroll
                     for (int i = 0; i < 4; ++i) { rows[i] = 4 * I + i; rows[4 + i] = 4 * Jb + i; }
-                    cf y[8][EPL], z[8][EPL];
+                    cf v[8][EPL];                  // first the Y rows, later re-used for the Z rows
                     float a[8];
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const cf* yr = Ys + (size_t)rows[i] * LS;
-                        const bool zr_ok = rows[i] < nv;
-                        const cf* zr = zr_ok ? zrow(rows[i]) : Ys;
                         float s2 = 0.f;
 #pragma unroll
                         for (int t = 0; t < EPL; ++t) {
-                            y[i][t] = (t < ylanes) ? yr[lane + 32 * t] : cf_make(0.f, 0.f);
-                            z[i][t] = (zr_ok && t < zlanes) ? zr[lane + 32 * t] : cf_make(0.f, 0.f);
-                            s2 += cf_abs2(y[i][t]);
+                            v[i][t] = (t < ylanes) ? yr[lane + 32 * t] : cf_make(0.f, 0.f);
+                            s2 += cf_abs2(v[i][t]);
                         }
                         a[i] = s2;
                     }
@@ -295,28 +322,54 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
                     int nrot = 0;
-                    if (r == 0) {
-                        { const int A_[4] = {0, 2, 4, 6}, B_[4] = {1, 3, 5, 7}; nrot += sub_round<4>(y, z, a, A_, B_, P.tol2); }
-                        { const int A_[4] = {0, 1, 4, 5}, B_[4] = {2, 3, 6, 7}; nrot += sub_round<4>(y, z, a, A_, B_, P.tol2); }
-                        { const int A_[4] = {0, 1, 4, 5}, B_[4] = {3, 2, 7, 6}; nrot += sub_round<4>(y, z, a, A_, B_, P.tol2); }
+                    const bool intra = (r == 0);
+                    if (intra) {
+                        nrot += sub_round_y<0, 2, 4, 6, 1, 3, 5, 7>(v, a, P.tol2, rot, 0, lane);
+                        nrot += sub_round_y<0, 1, 4, 5, 2, 3, 6, 7>(v, a, P.tol2, rot, 4, lane);
+                        nrot += sub_round_y<0, 1, 4, 5, 3, 2, 7, 6>(v, a, P.tol2, rot, 8, lane);
                     }
-                    { const int A_[4] = {0, 1, 2, 3}, B_[4] = {4, 5, 6, 7}; nrot += sub_round<4>(y, z, a, A_, B_, P.tol2); }
-                    { const int A_[4] = {0, 1, 2, 3}, B_[4] = {5, 6, 7, 4}; nrot += sub_round<4>(y, z, a, A_, B_, P.tol2); }
-                    { const int A_[4] = {0, 1, 2, 3}, B_[4] = {6, 7, 4, 5}; nrot += sub_round<4>(y, z, a, A_, B_, P.tol2); }
-                    { const int A_[4] = {0, 1, 2, 3}, B_[4] = {7, 4, 5, 6}; nrot += sub_round<4>(y, z, a, A_, B_, P.tol2); }
+                    nrot += sub_round_y<0, 1, 2, 3, 4, 5, 6, 7>(v, a, P.tol2, rot, 12, lane);
+                    nrot += sub_round_y<0, 1, 2, 3, 5, 6, 7, 4>(v, a, P.tol2, rot, 16, lane);
+                    nrot += sub_round_y<0, 1, 2, 3, 6, 7, 4, 5>(v, a, P.tol2, rot, 20, lane);
+                    nrot += sub_round_y<0, 1, 2, 3, 7, 4, 5, 6>(v, a, P.tol2, rot, 24, lane);
                     if (nrot) {
 #pragma unroll
                         for (int i = 0; i < 8; ++i) {
                             cf* yr = Ys + (size_t)rows[i] * LS;
-                            const bool zr_ok = rows[i] < nv;
-                            cf* zr = zr_ok ? zrow(rows[i]) : Ys;
 #pragma unroll
-                            for (int t = 0; t < EPL; ++t) {
-                                if (t < ylanes) yr[lane + 32 * t] = y[i][t];
-                                if (zr_ok && t < zlanes) zr[lane + 32 * t] = z[i][t];
+                            for (int t = 0; t < EPL; ++t)
+                                if (t < ylanes) yr[lane + 32 * t] = v[i][t];
+                        }
+                        // Z phase: same registers, rotations replayed from the log
+                        __syncwarp();
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            const bool ok = rows[i] < nv;
+                            const cf* zr = ok ? zrow(rows[i]) : Ys;
+#pragma unroll
+                            for (int t = 0; t < EPL; ++t)
+                                v[i][t] = (ok && t < zlanes) ? zr[lane + 32 * t] : cf_make(0.f, 0.f);
+                        }
+                        if (intra) {
+                            sub_round_z<0, 2, 4, 6, 1, 3, 5, 7>(v, rot, 0);
+                            sub_round_z<0, 1, 4, 5, 2, 3, 6, 7>(v, rot, 4);
+                            sub_round_z<0, 1, 4, 5, 3, 2, 7, 6>(v, rot, 8);
+                        }
+                        sub_round_z<0, 1, 2, 3, 4, 5, 6, 7>(v, rot, 12);
+                        sub_round_z<0, 1, 2, 3, 5, 6, 7, 4>(v, rot, 16);
+                        sub_round_z<0, 1, 2, 3, 6, 7, 4, 5>(v, rot, 20);
+                        sub_round_z<0, 1, 2, 3, 7, 4, 5, 6>(v, rot, 24);
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) {
+                            if (rows[i] < nv) {
+                                cf* zr = zrow(rows[i]);
+#pragma unroll
+                                for (int t = 0; t < EPL; ++t)
+                                    if (t < zlanes) zr[lane + 32 * t] = v[i][t];
                             }
                         }
                         my_rot += nrot;
+                        __syncwarp();              // the log is rewritten by the next group step
                     }
                 }
                 __syncthreads();
@@ -390,7 +443,7 @@ Layout make_layout(int nv, int L) {
     lo.nvp = (nv + 7) / 8 * 8;
     lo.LC = (L + 31) / 32 * 32; lo.LS = lo.LC + 1;
     lo.ZC = (nv + 31) / 32 * 32; lo.ZS = lo.ZC + 1;
-    size_t fixed = (size_t)lo.nvp * lo.LS * 8 + (size_t)2 * lo.nvp * 8 + (size_t)lo.nvp * 8 + 8 * 4 + 2 * 4 + 64;
+    size_t fixed = (size_t)NW * NSLOT * 16 + (size_t)lo.nvp * lo.LS * 8 + (size_t)2 * lo.nvp * 8 + (size_t)lo.nvp * 8 + NW * 4 + 2 * 4 + 64;
     int dev = 0, optin = 0;
     cudaGetDevice(&dev);
     if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || optin <= 0)
