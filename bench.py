@@ -45,7 +45,7 @@ def parse_args():
     p.add_argument("--chi", type=int, default=64)
     p.add_argument("--cpu-baseline-circuits", type=int, default=1)
     p.add_argument("--no-cpu-baseline", action="store_true")
-    p.add_argument("--extra", action="store_true", help="also time the chi=256 single-MPS config")
+    p.add_argument("--no-extra", action="store_true", help="skip the chi=256 single-chain timing")
     return p.parse_args()
 
 
@@ -260,6 +260,79 @@ def time_dominant_kernel(torch, args, batch, reps=3):
     return {"ms_per_launch": ms, "jobs_per_launch": nj, "m": m, "n": m, "mean_sweeps": sweeps}
 
 
+def time_secondary(torch, args, batch):
+    """Device-timed numbers for the other kernels of the path (CUDA events, same run)."""
+    from mpsim_b200 import _lib
+    lib = _lib.load(require_device=True)
+    chain = batch._chain
+    d, chi, B = 2, args.chi, chain.B
+    out = {}
+
+    def ev(fn, reps=5):
+        fn(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record(); torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    site = next((i for i in range(chain.n - 1)
+                 if chain.bonds[i] == chi and chain.bonds[i + 1] == chi and chain.bonds[i + 2] == chi), None)
+    if site is not None:
+        gates = torch.from_numpy(haar_gates(B, np.random.default_rng(7)).reshape(B, 16)).to(chain.device)
+        desc = np.zeros(1, dtype=_lib.GATE2_DESC)
+        desc[0] = (chain.site_ptr(site), chain.site_ptr(site + 1), 0, 0, gates.data_ptr(), 0,
+                   chain.total, chain.total, 0, 0, 16, 0)
+        ddesc = _lib.to_device_bytes(desc, chain.device)
+        m = d * chi
+        theta = torch.empty((B, m, m), dtype=torch.complex64, device=chain.device)
+        ms = ev(lambda: _lib.check(lib.mpsb_theta(ddesc.data_ptr(), 1, B, d, chi, chi, chi, theta.data_ptr(), None, 0,
+                                                  _lib.stream_ptr())))
+        fl = flops_theta(d, chi, chi, chi) * B
+        out["theta_kernel"] = {"ms_per_launch": ms, "jobs": B, "tflops": fl / (ms * 1e-3) / 1e12,
+                               "note": "split-real FFMA tiles (round 1); flops = 8 d^2 chi^3 + 8 d^4 chi^2 per application"}
+        # one-qudit gate on that site of every member: 16*d*chiL*chiR bytes per site
+        g1 = torch.from_numpy(np.tile(np.array([1, 1, 1, -1], dtype=np.complex64) / np.sqrt(2), (B, 1))).to(chain.device)
+        d1 = np.zeros(1, dtype=_lib.GATE1_DESC)
+        d1[0] = (chain.site_ptr(site), chain.site_ptr(site), g1.data_ptr(), chain.total, chain.total, 4, chi, chi)
+        dd1 = _lib.to_device_bytes(d1, chain.device)
+        ms = ev(lambda: _lib.check(lib.mpsb_apply_gate1(dd1.data_ptr(), 1, B, d, chi * d * chi, _lib.stream_ptr())))
+        out["gate1_kernel"] = {"ms_per_launch": ms, "gbs": 16.0 * d * chi * chi * B / (ms * 1e-3) / 1e9,
+                               "note": "one site (chi x 2 x chi) of every batch member: small launch, latency bound"}
+    ms = ev(lambda: chain.norms(), reps=3)
+    site_bytes = sum(8.0 * chain.site_elems(i) for i in range(chain.n)) * B
+    out["norm_chain"] = {"ms": ms, "launches": 2 * chain.n + 2, "gbs_sites_read_once": site_bytes / (ms * 1e-3) / 1e9}
+    return out
+
+
+def time_chi256(torch):
+    """BASELINE.json configs[2]: 100-qubit brickwork, depth 20, chi = 256, one chain (replicas only)."""
+    import mpsim_b200 as mp
+    from mpsim_b200 import circuits
+    from mpsim_b200.planner import plan_operations
+    n, depth, chi = 100, 20, 256
+    ops = circuits.brickwork(n, depth, seed=3)
+    mps = mp.MPS(n)
+    plan = plan_operations(n, 2, mps._chain.bonds,
+                           [(o.tensor, o.indices, {"maxsvals": chi, "keep_left_canonical": o.keep_left_canonical}) for o in ops])
+    cp = mps._chain.compile(plan)
+    mps._chain.run(cp)
+    torch.cuda.synchronize()
+    mps._chain.reset()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    mps._chain.run(cp, upload=False)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    info = cp.info.cpu().numpy()[: len(plan.apps2)]
+    fl = sum(flops_svd_lapack(2 * a.chiL, 2 * a.chiR) + flops_theta(2, a.chiL, a.chiM, a.chiR) for a in plan.apps2)
+    return {"workload": "100-qubit brickwork depth 20 chi=256 (BASELINE.json configs[2]), one chain",
+            "applications": len(plan.apps2), "ms": ms, "applications_per_sec": len(plan.apps2) / (ms * 1e-3),
+            "lapack_equivalent_tflops": fl / (ms * 1e-3) / 1e12,
+            "svd_not_converged": int((info[:, 0] != 0).sum()), "svd_mean_sweeps": float(info[:, 1].mean())}
+
+
 def measure_fp32_peak(torch):
     """FP32 FFMA peak of this GPU measured live with torch (dependent-free FMA chains are not
     expressible in torch; use a large fp32 GEMM through cuBLAS as the FFMA proxy)."""
@@ -391,6 +464,11 @@ def run_our_arm(args):
                             "not HBM bound",
                     "ms_per_launch": dom["ms_per_launch"], "jobs_per_launch": dom["jobs_per_launch"],
                     "mean_sweeps": dom["mean_sweeps"]}
+        secondary = time_secondary(torch, args, batch)
+        if not args.no_extra:
+            del batch
+            torch.cuda.empty_cache()
+            secondary["chi256"] = time_chi256(torch)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -417,6 +495,7 @@ def run_our_arm(args):
             "gpu_launches": launches_per_step * args.steps,
             "roofline": roof,
             "cpu_baseline": cpu,
+            "secondary": secondary,
             "applications_per_step": apps_per_step_total,
             "svd_not_converged": not_converged, "svd_mean_sweeps": mean_sweeps,
             "norm_mean": float(norms_all.float().mean().item()),
