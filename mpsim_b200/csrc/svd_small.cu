@@ -76,7 +76,7 @@ __device__ __forceinline__ void rot_apply(float c, float sr, float si, cf& p, cf
 }
 
 // One sub-round on the Y rows of a group: 4 disjoint pairs (A_i, B_i).  The four Gram entries are
-// reduced together; lane l then computes the rotation of pair (l & 3) only and the parameters
+// reduced together; lane l then computes the rotation of pair (l >> 3) only and the parameters
 // are exchanged by shuffles (4x fewer scalar instructions than every lane doing all four).
 // The rotations are logged to rot[slot..slot+3] = (c, s.re, s.im, rotated?) for the Z phase.
 template <int A0, int A1, int A2, int A3, int B0, int B1, int B2, int B3>
@@ -95,35 +95,56 @@ __device__ __forceinline__ int sub_round_y(cf (&y)[8][EPL], float (&a)[8], float
         }
         gr[i] = r; gi[i] = m;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            gr[i] += __shfl_xor_sync(0xffffffffu, gr[i], o);
-            gi[i] += __shfl_xor_sync(0xffffffffu, gi[i], o);
-        }
+    // Transposed reduction: 12 shuffles instead of 40.  After the 16- and 8-steps every lane
+    // owns ONE of the four pairs (pair index = lane >> 3), the 4/2/1 butterfly finishes it.
+    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0;
+    float mgr, mgi;
+    {
+        float k0 = h16 ? gr[2] : gr[0], k1 = h16 ? gr[3] : gr[1];
+        float s0 = h16 ? gr[0] : gr[2], s1 = h16 ? gr[1] : gr[3];
+        k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        float k = h8 ? k1 : k0, sd = h8 ? k0 : k1;
+        k += __shfl_xor_sync(0xffffffffu, sd, 8);
+        k += __shfl_xor_sync(0xffffffffu, k, 4);
+        k += __shfl_xor_sync(0xffffffffu, k, 2);
+        k += __shfl_xor_sync(0xffffffffu, k, 1);
+        mgr = k;
     }
-    // this lane's pair
-    const int sel = lane & 3;
-    float mgr = gr[0], mgi = gi[0], ap = a[PA[0]], aq = a[PB[0]];
+    {
+        float k0 = h16 ? gi[2] : gi[0], k1 = h16 ? gi[3] : gi[1];
+        float s0 = h16 ? gi[0] : gi[2], s1 = h16 ? gi[1] : gi[3];
+        k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+        k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+        float k = h8 ? k1 : k0, sd = h8 ? k0 : k1;
+        k += __shfl_xor_sync(0xffffffffu, sd, 8);
+        k += __shfl_xor_sync(0xffffffffu, k, 4);
+        k += __shfl_xor_sync(0xffffffffu, k, 2);
+        k += __shfl_xor_sync(0xffffffffu, k, 1);
+        mgi = k;
+    }
+    // this lane's pair: index lane >> 3 (all 8 lanes of an octet hold bitwise identical sums)
+    const int sel = lane >> 3;
+    float ap = a[PA[0]], aq = a[PB[0]];
 #pragma unroll
     for (int i = 1; i < 4; ++i) {
-        if (sel == i) { mgr = gr[i]; mgi = gi[i]; ap = a[PA[i]]; aq = a[PB[i]]; }
+        if (sel == i) { ap = a[PA[i]]; aq = a[PB[i]]; }
     }
     const float g2 = fmaf(mgr, mgr, mgi * mgi);
     float c = 1.f, sr = 0.f, si = 0.f, tg = 0.f;
     const bool dorot = (g2 > tol2 * ap * aq) && (g2 > 1e-30f);
     if (dorot) rot_params(ap, aq, mgr, mgi, g2, c, sr, si, tg);
-    if (lane < 4) rot[slot + lane] = make_float4(c, sr, si, dorot ? 1.f : 0.f);
-    const unsigned flags = __ballot_sync(0xffffffffu, dorot) & 0xFu;
+    if ((lane & 7) == 0) rot[slot + sel] = make_float4(c, sr, si, dorot ? 1.f : 0.f);
+    const unsigned bal = __ballot_sync(0xffffffffu, dorot);
+    const unsigned flags = (bal & 1u) | ((bal >> 7) & 2u) | ((bal >> 14) & 4u) | ((bal >> 21) & 8u);
     if (flags == 0u) return 0;
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         if (flags & (1u << i)) {                       // warp-uniform
-            const float ci = __shfl_sync(0xffffffffu, c, i);
-            const float sri = __shfl_sync(0xffffffffu, sr, i);
-            const float sii = __shfl_sync(0xffffffffu, si, i);
-            const float tgi = __shfl_sync(0xffffffffu, tg, i);
+            const float ci = __shfl_sync(0xffffffffu, c, 8 * i);
+            const float sri = __shfl_sync(0xffffffffu, sr, 8 * i);
+            const float sii = __shfl_sync(0xffffffffu, si, 8 * i);
+            const float tgi = __shfl_sync(0xffffffffu, tg, 8 * i);
 #pragma unroll
             for (int t = 0; t < EPL; ++t) rot_apply(ci, sri, sii, y[PA[i]][t], y[PB[i]][t]);
             a[PA[i]] = fmaxf(a[PA[i]] + tgi, 0.f);
@@ -240,31 +261,55 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
                 tau = 1.0f / (normx * (normx + ax0));
             }
             const bool upd = reflect && ((isY && col > j) || isZ);
-            // pass 1: w = v^H A[:, col] over this thread's rows (j + half, j + half + 2, ...)
+            // This thread's rows are j + half, j + half + 2, ...; row j (v0 instead of vb[j]) belongs
+            // to half == 0.  A Z column is split at nzs into its shared-memory and its spilled part
+            // so that the loops run on plain pointers with constant strides.
+            const int ifirst = j + half + (half == 0 ? 2 : 0);      // first row handled with vb[]
+            const int zsplit = min(nv, max(ifirst, nzs + ((nzs ^ ifirst) & 1)));   // first spilled row of my parity
+            cf* prow_j = isY ? &Ys[(size_t)j * LS + col] : &zrow(j)[col];
+            // pass 1: w = v^H A[:, col]
             cf w = cf_make(0.f, 0.f);
             if (upd) {
-                for (int i = j + half; i < nv; i += 2) {
-                    cf vi = (i == j) ? v0 : vb[i];
-                    cf aij = isY ? Ys[(size_t)i * LS + col] : zrow(i)[col];
-                    w = cf_fma_conja(vi, aij, w);
+                if (half == 0) w = cf_fma_conja(v0, *prow_j, w);
+                if (isY) {
+                    const cf* a = Ys + (size_t)ifirst * LS + col;
+                    for (int i = ifirst; i < nv; i += 2, a += 2 * LS) w = cf_fma_conja(vb[i], *a, w);
+                } else {
+                    const cf* a = Zs + (size_t)ifirst * ZS + col;
+                    int i = ifirst;
+                    for (; i < zsplit; i += 2, a += 2 * ZS) w = cf_fma_conja(vb[i], *a, w);
+                    const cf* b = zg + (size_t)(i - nzs) * ZS + col;
+                    for (; i < nv; i += 2, b += 2 * ZS) w = cf_fma_conja(vb[i], *b, w);
                 }
             }
             w.x += __shfl_xor_sync(0xffffffffu, w.x, 1);
             w.y += __shfl_xor_sync(0xffffffffu, w.y, 1);
-            // pass 2: A[:, col] -= tau v w ; the owner of column j+1 records the next reflector
+            // pass 2: A[:, col] -= tau v w ; the owner of column j+1 also records the next reflector
             float t2 = 0.f;
             if (upd) {
-                cf tw = cf_scale(-tau, w);
-                for (int i = j + half; i < nv; i += 2) {
-                    cf vi = (i == j) ? v0 : vb[i];
-                    cf* pa = isY ? &Ys[(size_t)i * LS + col] : &zrow(i)[col];
-                    cf nvl = cf_fma(vi, tw, *pa);
-                    *pa = nvl;
-                    if (record && i > j) {
+                const cf tw = cf_scale(-tau, w);
+                if (half == 0) *prow_j = cf_fma(v0, tw, *prow_j);
+                if (record) {
+                    cf* a = Ys + (size_t)ifirst * LS + col;
+                    if (half == 1) {                       // row j+1 is mine: it is the next x0
+                        // (ifirst == j + 1 for half == 1)
+                    }
+                    for (int i = ifirst; i < nv; i += 2, a += 2 * LS) {
+                        cf nvl = cf_fma(vb[i], tw, *a);
+                        *a = nvl;
                         vn[i] = nvl;
                         if (i > j + 1) t2 += cf_abs2(nvl);
                         else { scal[nxt * 4 + 0] = nvl.x; scal[nxt * 4 + 1] = nvl.y; }
                     }
+                } else if (isY) {
+                    cf* a = Ys + (size_t)ifirst * LS + col;
+                    for (int i = ifirst; i < nv; i += 2, a += 2 * LS) *a = cf_fma(vb[i], tw, *a);
+                } else {
+                    cf* a = Zs + (size_t)ifirst * ZS + col;
+                    int i = ifirst;
+                    for (; i < zsplit; i += 2, a += 2 * ZS) *a = cf_fma(vb[i], tw, *a);
+                    cf* b = zg + (size_t)(i - nzs) * ZS + col;
+                    for (; i < nv; i += 2, b += 2 * ZS) *b = cf_fma(vb[i], tw, *b);
                 }
             } else if (reflect && isY && col == j) {
                 for (int i = j + half; i < nv; i += 2) Ys[(size_t)i * LS + j] = (i == j) ? alpha : cf_make(0.f, 0.f);
