@@ -5,24 +5,29 @@
 //
 // Input  X [nv][L] : the theta matrix oriented so that its ROWS are the vectors to
 //                    orthogonalise (left-canonical: X = theta, nv = d*chiL, L = d*chiR;
-//                    otherwise X = theta^T).
-// Method (CPU model with identical arithmetic: tests/_jacobi_model.py):
-//   1. Householder QR preconditioning  X = Q R ; Y <- R, Z <- Q^H.  Jacobi on R converges in
-//      ~9 sweeps independently of how graded the spectrum is (plain Jacobi on X needs 15-25).
-//   2. One-sided Jacobi on the rows of Y, the same 2x2 unitaries accumulated into Z, so that
-//      Z X0 == Y always.  Rows are visited by a block tournament: 4-row blocks are paired by the
-//      circle method; a warp owns a pair of blocks, keeps its 8 rows of Y in registers
-//      (lane owns elements lane, lane+32, ...), performs the 16 cross rotations (plus the 12
-//      intra-block ones in the first round of a sweep) with warp-shuffle reductions, logs them
-//      to shared memory and replays them on its 8 rows of Z in the same registers (two phases
-//      keep the kernel under 128 registers, so 16 warps are resident instead of 8).
+//                    otherwise X = theta^T).  X = U S V^H below.
+// Method (CPU model of the same algorithm: tests/_jacobi_model.py):
+//   0. Y = X scaled by an exact power of two so that max|x| is in [1, 2).
+//   1. Householder QR preconditioning, R only (Y <- R): Jacobi on R converges in ~8 sweeps
+//      independently of how graded the spectrum is (plain Jacobi on X needs 10-25).
+//   2. One-sided Jacobi on the rows of Y (Y <- J Y, J unitary, never formed).  Rows are visited by
+//      a block tournament: 4-row blocks are paired by the circle method; a warp owns a pair of
+//      blocks, keeps its 8 rows in registers (lane owns elements lane, lane+32, ...) and performs
+//      the 16 cross rotations (plus the 12 intra-block ones in the first round of a sweep) with
+//      transposed warp-shuffle reductions; squared row norms are cached in shared memory and
+//      refreshed once per sweep.  At convergence row j of Y is sigma_j v_j^H.
 //   3. sigma_j = |Y_j|, stable descending rank sort (ties keep the lower index: this is what
 //      reproduces the reference on Bell + maxsvals=1, README.md:48-53), keep the first k.
-//   4. Split/absorb without any division: the isometry is conj(Z) (a product of unitaries, so
-//      orthonormal even for zero singular values, like LAPACK's), the weighted factor is Y:
-//        left-canonical : left  = Z_k^H   (U)     right = Y_k      (S.Vh)
-//        otherwise      : left  = Y_k^T   (U.S)   right = conj(Z_k) (Vh)
-//      left.right == exact rank-k projection of theta whether or not Jacobi converged.
+//   4. Isometry without accumulating J and without dividing by small numbers that matter:
+//        W = X V_k  (columns sigma_j u_j, rescaled by 1/sigma_j; columns with sigma_j ~ 0 are set to 0),
+//        Q = the first k columns of the unitary of a Householder QR of W (formed in place).
+//      Q is a product of reflectors applied to [I_k; 0], hence orthonormal to rounding even in
+//      the null directions (like LAPACK's U), and because the columns of W come in descending
+//      sigma order, span(Q[:, :j]) = span(u_1..u_j) for every j.
+//   5. Split/absorb:  P = Q^H X  (k x L), so that  Q P  is the exact orthogonal projection of X
+//      onto span(U_k) whether or not Jacobi converged:
+//        left-canonical : left = Q        (U)     right = P      (S.Vh)
+//        otherwise      : left = P^T      (U.S)   right = Q^T    (Vh; X was theta^T)
 #include "common.cuh"
 #include <stdlib.h>
 
@@ -31,14 +36,14 @@ namespace {
 constexpr int ST = 512;          // threads per CTA
 constexpr int NW = ST / 32;      // warps: one 8-row group each at nv = 128
 constexpr int EPL = 4;           // elements per lane per row (row length <= 128)
-constexpr int NSLOT = 28;        // rotations per group step: 12 intra-block + 16 cross
+constexpr int XCH = 32;          // staging chunk of X: columns in step 4, rows in step 5
+constexpr int XS_ELEMS = 128 * (XCH + 1);   // >= XCH * (128 + 4)
+constexpr float BIG2 = 1e-4f * 1e-4f;       // a sweep without a rotation above this is the last
 
 struct SvdSmallParams {
     const cf* X; int64_t x_stride;
     int nv, L, k, lc;
-    int nvp, LS, ZS, LC, ZC;     // padded rows, smem strides, columns touched by lanes
-    int nz_smem;                 // Z rows [0, nz_smem) live in shared memory, the rest in zg
-    cf* zg; int64_t zg_stride;
+    int nvp, LS, LC;             // padded rows, smem row stride, columns touched by lanes
     const mpsb_gate2_desc* descs; int nbatch;     // output mode A (descs != nullptr)
     cf* left; int64_t left_stride; cf* right; int64_t right_stride;   // output mode B
     float* svals; int64_t svals_stride;
@@ -75,13 +80,11 @@ __device__ __forceinline__ void rot_apply(float c, float sr, float si, cf& p, cf
     q = nq_;
 }
 
-// One sub-round on the Y rows of a group: 4 disjoint pairs (A_i, B_i).  The four Gram entries are
+// One sub-round on the rows of a group: 4 disjoint pairs (A_i, B_i).  The four Gram entries are
 // reduced together; lane l then computes the rotation of pair (l >> 3) only and the parameters
 // are exchanged by shuffles (4x fewer scalar instructions than every lane doing all four).
-// The rotations are logged to rot[slot..slot+3] = (c, s.re, s.im, rotated?) for the Z phase.
 template <int A0, int A1, int A2, int A3, int B0, int B1, int B2, int B3>
-__device__ __forceinline__ int sub_round_y(cf (&y)[8][EPL], float (&a)[8], float tol2,
-                                           float4* rot, int slot, int lane) {
+__device__ __forceinline__ int sub_round_y(cf (&y)[8][EPL], float (&a)[8], float tol2, int lane, bool& big) {
     constexpr int PA[4] = {A0, A1, A2, A3}, PB[4] = {B0, B1, B2, B3};
     float gr[4], gi[4];
 #pragma unroll
@@ -131,10 +134,11 @@ __device__ __forceinline__ int sub_round_y(cf (&y)[8][EPL], float (&a)[8], float
         if (sel == i) { ap = a[PA[i]]; aq = a[PB[i]]; }
     }
     const float g2 = fmaf(mgr, mgr, mgi * mgi);
+    const float apq = ap * aq;
     float c = 1.f, sr = 0.f, si = 0.f, tg = 0.f;
-    const bool dorot = (g2 > tol2 * ap * aq) && (g2 > 1e-30f);
+    const bool dorot = (g2 > tol2 * apq) && (g2 > 1e-30f);
+    big = big || (dorot && g2 > BIG2 * apq);
     if (dorot) rot_params(ap, aq, mgr, mgi, g2, c, sr, si, tg);
-    if ((lane & 7) == 0) rot[slot + sel] = make_float4(c, sr, si, dorot ? 1.f : 0.f);
     const unsigned bal = __ballot_sync(0xffffffffu, dorot);
     const unsigned flags = (bal & 1u) | ((bal >> 7) & 2u) | ((bal >> 14) & 4u) | ((bal >> 21) & 8u);
     if (flags == 0u) return 0;
@@ -154,17 +158,169 @@ __device__ __forceinline__ int sub_round_y(cf (&y)[8][EPL], float (&a)[8], float
     return __popc(flags);
 }
 
-// The same sub-round replayed on the Z rows from the logged rotations.
-template <int A0, int A1, int A2, int A3, int B0, int B1, int B2, int B3>
-__device__ __forceinline__ void sub_round_z(cf (&z)[8][EPL], const float4* rot, int slot) {
-    constexpr int PA[4] = {A0, A1, A2, A3}, PB[4] = {B0, B1, B2, B3};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const float4 r = rot[slot + i];                // broadcast load
-        if (r.w != 0.f) {
-#pragma unroll
-            for (int t = 0; t < EPL; ++t) rot_apply(r.x, r.y, r.z, z[PA[i]][t], z[PB[i]][t]);
+// threads per column for the Householder passes: the largest power of two <= 32 with ncols * tpc <= ST
+__device__ __forceinline__ int threads_per_col(int ncols) {
+    int t = 32;
+    while (t > 1 && ncols * t > ST) t >>= 1;
+    return t;
+}
+
+__device__ __forceinline__ cf group_sum(cf w, int tpc) {
+    for (int o = tpc >> 1; o > 0; o >>= 1) {
+        w.x += __shfl_xor_sync(0xffffffffu, w.x, o);
+        w.y += __shfl_xor_sync(0xffffffffu, w.y, o);
+    }
+    return w;
+}
+
+// Householder reduction of A [nrows][ncols] (row stride LS), steps j = 0..nsteps-1, one barrier per
+// step: the threads of column j+1 record the next reflector while they update their column.
+//   STORE = 0 : A <- R (alpha on the diagonal, zeros below); reflectors are dropped.
+//   STORE = 1 : column j, rows j.. keep the reflector v_j (v_j[0] on the diagonal), tau[j] its
+//               scale (0 = identity): H_j = I - tau v v^H.
+// tpc threads share a column (rows interleaved).  vbuf [2][nvp], scal [8].
+template <int STORE>
+__device__ void householder_forward(cf* A, int LS, int nrows, int ncols, int nsteps, cf* vbuf, int nvp,
+                                    float* scal, float* tau_arr) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (nsteps <= 0) return;
+    const int tpc = threads_per_col(ncols);
+    if (warp == 0) {
+        float t2 = 0.f;
+        for (int i = lane; i < nrows; i += 32) {
+            cf v = A[(size_t)i * LS];
+            vbuf[i] = v;
+            if (i > 0) t2 += cf_abs2(v);
         }
+        t2 = warp_sum(t2);
+        if (lane == 0) { cf x0 = A[0]; scal[0] = x0.x; scal[1] = x0.y; scal[2] = t2; }
+    }
+    __syncthreads();
+    const int col = tid / tpc, sub = tid % tpc;
+    const bool mine = col < ncols;
+    for (int j = 0; j < nsteps; ++j) {
+        const int cur = j & 1, nxt = cur ^ 1;
+        const cf* vb = vbuf + cur * nvp;
+        cf* vn = vbuf + nxt * nvp;
+        cf x0 = cf_make(scal[cur * 4 + 0], scal[cur * 4 + 1]);
+        const float tail2 = scal[cur * 4 + 2];
+        const bool record = mine && (col == j + 1) && (j + 1 < nsteps);
+        float ax0sq = cf_abs2(x0);
+        // |x0|^2 below ~1e-30 is a denormal-range number with few significant bits: the
+        // phase x0/|x0| would be off by 1e-4 and the reflector no longer unitary (seen on
+        // GHZ circuits).  The matrix is scaled to max|x| in [1,2), so such an x0 is noise.
+        if (ax0sq < 1e-30f) { x0 = cf_make(0.f, 0.f); ax0sq = 0.f; }
+        // skip the reflector when the column is already reduced (keeps diagonal inputs, and with
+        // them the order of tied singular values, untouched), or so small that 1/|x|^2 overflows
+        const bool reflect = tail2 > 0.f && tail2 + ax0sq > 1e-30f;
+        cf v0 = cf_make(0.f, 0.f), alpha = cf_make(0.f, 0.f);
+        float tau = 0.f;
+        if (reflect) {
+            float ax0 = sqrtf(ax0sq);
+            float normx = sqrtf(tail2 + ax0sq);
+            cf ph = ax0 > 0.f ? cf_scale(1.0f / ax0, x0) : cf_make(1.f, 0.f);
+            alpha = cf_scale(-normx, ph);
+            v0 = cf_sub(x0, alpha);
+            tau = 1.0f / (normx * (normx + ax0));
+        }
+        const bool upd = reflect && mine && col > j;
+        const int ifirst = j + sub + (sub == 0 ? tpc : 0);      // first of my rows handled with vb[]
+        cf* acol = A + col;
+        // pass 1: w = v^H A[:, col]
+        cf w = cf_make(0.f, 0.f);
+        if (upd) {
+            if (sub == 0) w = cf_fma_conja(v0, acol[(size_t)j * LS], w);
+            const cf* a = acol + (size_t)ifirst * LS;
+            for (int i = ifirst; i < nrows; i += tpc, a += (size_t)tpc * LS) w = cf_fma_conja(vb[i], *a, w);
+        }
+        w = group_sum(w, tpc);
+        // pass 2: A[:, col] -= tau v w
+        float t2 = 0.f;
+        if (upd) {
+            const cf tw = cf_scale(-tau, w);
+            if (sub == 0) acol[(size_t)j * LS] = cf_fma(v0, tw, acol[(size_t)j * LS]);
+            cf* a = acol + (size_t)ifirst * LS;
+            if (record) {
+                for (int i = ifirst; i < nrows; i += tpc, a += (size_t)tpc * LS) {
+                    cf nvl = cf_fma(vb[i], tw, *a);
+                    *a = nvl;
+                    vn[i] = nvl;
+                    if (i > j + 1) t2 += cf_abs2(nvl);
+                    else { scal[nxt * 4 + 0] = nvl.x; scal[nxt * 4 + 1] = nvl.y; }
+                }
+            } else {
+                for (int i = ifirst; i < nrows; i += tpc, a += (size_t)tpc * LS) *a = cf_fma(vb[i], tw, *a);
+            }
+        } else if (record) {                       // no reflector in this step: column j+1 as it is
+            for (int i = j + 1 + sub; i < nrows; i += tpc) {
+                cf v = acol[(size_t)i * LS];
+                vn[i] = v;
+                if (i > j + 1) t2 += cf_abs2(v);
+                else { scal[nxt * 4 + 0] = v.x; scal[nxt * 4 + 1] = v.y; }
+            }
+        } else if (mine && col == j) {
+            if (STORE) {
+                if (sub == 0) {
+                    tau_arr[j] = reflect ? tau : 0.f;
+                    if (reflect) acol[(size_t)j * LS] = v0;
+                }
+            } else if (reflect) {
+                for (int i = j + sub; i < nrows; i += tpc) acol[(size_t)i * LS] = (i == j) ? alpha : cf_make(0.f, 0.f);
+            }
+        }
+        {
+            cf t = group_sum(cf_make(t2, 0.f), tpc);
+            if (record && sub == 0) scal[nxt * 4 + 2] = t.x;
+        }
+        __syncthreads();
+    }
+}
+
+// A [nrows][k] holds the reflectors of householder_forward<1>; overwrite it with
+// Q = H_0 H_1 ... H_{k-1} [I_k; 0] (the unitary's first k columns), one barrier per step.
+__device__ void householder_form_q(cf* A, int LS, int nrows, int k, cf* vbuf, int nvp, const float* tau_arr) {
+    const int tid = threadIdx.x;
+    if (k <= 0) return;
+    const int tpc = threads_per_col(k);
+    const int col = tid / tpc, sub = tid % tpc;
+    const bool mine = col < k;
+    {
+        const int j = k - 1;
+        cf* vn = vbuf + (j & 1) * nvp;
+        for (int i = j + tid; i < nrows; i += ST) vn[i] = A[(size_t)i * LS + j];
+    }
+    __syncthreads();
+    for (int j = k - 1; j >= 0; --j) {
+        const cf* vb = vbuf + (j & 1) * nvp;
+        cf* vn = vbuf + ((j & 1) ^ 1) * nvp;
+        const float tau = tau_arr[j];
+        cf* acol = A + col;
+        cf w = cf_make(0.f, 0.f);
+        const bool upd = mine && col > j && tau != 0.f;
+        if (upd) {
+            const cf* a = acol + (size_t)(j + sub) * LS;
+            for (int i = j + sub; i < nrows; i += tpc, a += (size_t)tpc * LS) w = cf_fma_conja(vb[i], *a, w);
+        }
+        w = group_sum(w, tpc);
+        if (upd) {
+            const cf tw = cf_scale(-tau, w);
+            cf* a = acol + (size_t)(j + sub) * LS;
+            for (int i = j + sub; i < nrows; i += tpc, a += (size_t)tpc * LS) *a = cf_fma(vb[i], tw, *a);
+        } else if (mine && col == j) {
+            // H_j e_j = e_j - tau conj(v_j[0]) v_j ; rows above j still hold R from the forward pass
+            const cf f = (tau != 0.f) ? cf_scale(-tau, cf_conj(vb[j])) : cf_make(0.f, 0.f);
+            for (int i = sub; i < nrows; i += tpc) {
+                cf q = cf_make(0.f, 0.f);
+                if (i >= j) {
+                    if (tau != 0.f) q = cf_mul(f, vb[i]);
+                    if (i == j) q.x += 1.0f;
+                }
+                acol[(size_t)i * LS] = q;
+            }
+        } else if (mine && j > 0 && col == j - 1) {
+            for (int i = j - 1 + sub; i < nrows; i += tpc) vn[i] = acol[(size_t)i * LS];
+        }
+        __syncthreads();
     }
 }
 
@@ -172,21 +328,18 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
     extern __shared__ float4 smem_raw[];
     const int job = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nv = P.nv, L = P.L, nvp = P.nvp, LS = P.LS, ZS = P.ZS;
+    const int nv = P.nv, L = P.L, nvp = P.nvp, LS = P.LS, k = P.k;
 
-    float4* rotbuf = smem_raw;                     // [NW][NSLOT] (16-byte aligned first)
-    cf* Ys = (cf*)(rotbuf + NW * NSLOT);           // [nvp][LS]
-    cf* Zs = Ys + (size_t)nvp * LS;                // [nz_smem][ZS]
-    cf* vbuf = Zs + (size_t)P.nz_smem * ZS;        // [2][nvp]
-    float* sig = (float*)(vbuf + 2 * nvp);         // [nvp]
-    int* perm = (int*)(sig + nvp);                 // [nvp]
-    float* scal = (float*)(perm + nvp);            // [NW] (also the QR scalars: 8 used)
-    int* cnt = (int*)(scal + NW);                  // [2]
-    cf* zg = P.zg + (size_t)job * P.zg_stride;
-    const int nzs = P.nz_smem;
-    auto zrow = [&](int i) -> cf* { return i < nzs ? Zs + (size_t)i * ZS : zg + (size_t)(i - nzs) * ZS; };
+    cf* Ys = (cf*)smem_raw;                        // [nvp][LS]   Y, later W / Q
+    cf* Xs = Ys + (size_t)nvp * LS;                // [XS_ELEMS]  staging of X for steps 4, 5
+    cf* vbuf = Xs + XS_ELEMS;                      // [2][nvp]
+    float* sig = (float*)(vbuf + 2 * nvp);         // [nvp]  sigma (scaled units)
+    float* nrm = sig + nvp;                        // [nvp]  cached squared row norms
+    float* tau_arr = nrm + nvp;                    // [nvp]
+    int* perm = (int*)(tau_arr + nvp);             // [nvp]
+    float* scal = (float*)(perm + nvp);            // [NW]  (also the QR scalars: 8 used)
 
-    // ---- phase 0: load X scaled by an exact power of two so that max|x| is in [1, 2), Z = I ----
+    // ---- step 0: load X scaled by an exact power of two so that max|x| is in [1, 2) ----------
     // (the guards below are absolute, and products of numerical zeros would otherwise
     //  underflow in the Gram entries; LAPACK scales for the same reason)
     const cf* X = P.X + (size_t)job * P.x_stride;
@@ -210,226 +363,89 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
         if (i < nv && c < L) { v = X[(size_t)i * L + c]; v.x *= scale_in; v.y *= scale_in; }
         Ys[e] = v;
     }
-    for (int e = tid; e < nv * ZS; e += ST) {
-        int i = e / ZS, c = e - i * ZS;
-        zrow(i)[c] = cf_make(c == i ? 1.f : 0.f, 0.f);
-    }
-    if (tid < 2) cnt[tid] = 0;
     __syncthreads();
 
-    // ---- phase 1: Householder QR, two threads per column of [Y | Z] (rows split even/odd) ----
-    const int J = P.do_qr ? min(nv - 1, L) : 0;
-    if (J > 0) {
-        if (warp == 0) {
-            float t2 = 0.f;
-            for (int i = lane; i < nv; i += 32) {
-                cf v = Ys[(size_t)i * LS];
-                vbuf[i] = v;
-                if (i > 0) t2 += cf_abs2(v);
-            }
-            t2 = warp_sum(t2);
-            if (lane == 0) { cf x0 = Ys[0]; scal[0] = x0.x; scal[1] = x0.y; scal[2] = t2; }
-        }
-        __syncthreads();
-        const int colid = tid >> 1, half = tid & 1;
-        const bool isY = colid < L;
-        const bool isZ = !isY && (colid - L) < nv;
-        const int col = isY ? colid : colid - L;
-        for (int j = 0; j < J; ++j) {
-            const int cur = j & 1, nxt = cur ^ 1;
-            const cf* vb = vbuf + cur * nvp;
-            cf* vn = vbuf + nxt * nvp;
-            cf x0 = cf_make(scal[cur * 4 + 0], scal[cur * 4 + 1]);
-            const float tail2 = scal[cur * 4 + 2];
-            const bool record = isY && (col == j + 1) && (j + 1 < J);
-            float ax0sq = cf_abs2(x0);
-            // |x0|^2 below ~1e-30 is a denormal-range number with few significant bits: the
-            // phase x0/|x0| would be off by 1e-4 and the reflector no longer unitary (seen on
-            // GHZ circuits).  The matrix is scaled to max|x| in [1,2), so such an x0 is noise.
-            if (ax0sq < 1e-30f) { x0 = cf_make(0.f, 0.f); ax0sq = 0.f; }
-            // skip the reflector when the column is already reduced, or so small that
-            // 1/|x|^2 would overflow (QR is only a preconditioner: any unitary Z is valid)
-            const bool reflect = tail2 > 0.f && tail2 + ax0sq > 1e-30f;
-            cf v0 = cf_make(0.f, 0.f), alpha = cf_make(0.f, 0.f);
-            float tau = 0.f;
-            if (reflect) {
-                float ax0 = sqrtf(ax0sq);
-                float normx = sqrtf(tail2 + ax0sq);
-                cf ph = ax0 > 0.f ? cf_scale(1.0f / ax0, x0) : cf_make(1.f, 0.f);
-                alpha = cf_scale(-normx, ph);
-                v0 = cf_sub(x0, alpha);
-                tau = 1.0f / (normx * (normx + ax0));
-            }
-            const bool upd = reflect && ((isY && col > j) || isZ);
-            // This thread's rows are j + half, j + half + 2, ...; row j (v0 instead of vb[j]) belongs
-            // to half == 0.  A Z column is split at nzs into its shared-memory and its spilled part
-            // so that the loops run on plain pointers with constant strides.
-            const int ifirst = j + half + (half == 0 ? 2 : 0);      // first row handled with vb[]
-            const int zsplit = min(nv, max(ifirst, nzs + ((nzs ^ ifirst) & 1)));   // first spilled row of my parity
-            cf* prow_j = isY ? &Ys[(size_t)j * LS + col] : &zrow(j)[col];
-            // pass 1: w = v^H A[:, col]
-            cf w = cf_make(0.f, 0.f);
-            if (upd) {
-                if (half == 0) w = cf_fma_conja(v0, *prow_j, w);
-                if (isY) {
-                    const cf* a = Ys + (size_t)ifirst * LS + col;
-                    for (int i = ifirst; i < nv; i += 2, a += 2 * LS) w = cf_fma_conja(vb[i], *a, w);
-                } else {
-                    const cf* a = Zs + (size_t)ifirst * ZS + col;
-                    int i = ifirst;
-                    for (; i < zsplit; i += 2, a += 2 * ZS) w = cf_fma_conja(vb[i], *a, w);
-                    const cf* b = zg + (size_t)(i - nzs) * ZS + col;
-                    for (; i < nv; i += 2, b += 2 * ZS) w = cf_fma_conja(vb[i], *b, w);
-                }
-            }
-            w.x += __shfl_xor_sync(0xffffffffu, w.x, 1);
-            w.y += __shfl_xor_sync(0xffffffffu, w.y, 1);
-            // pass 2: A[:, col] -= tau v w ; the owner of column j+1 also records the next reflector
-            float t2 = 0.f;
-            if (upd) {
-                const cf tw = cf_scale(-tau, w);
-                if (half == 0) *prow_j = cf_fma(v0, tw, *prow_j);
-                if (record) {
-                    cf* a = Ys + (size_t)ifirst * LS + col;
-                    if (half == 1) {                       // row j+1 is mine: it is the next x0
-                        // (ifirst == j + 1 for half == 1)
-                    }
-                    for (int i = ifirst; i < nv; i += 2, a += 2 * LS) {
-                        cf nvl = cf_fma(vb[i], tw, *a);
-                        *a = nvl;
-                        vn[i] = nvl;
-                        if (i > j + 1) t2 += cf_abs2(nvl);
-                        else { scal[nxt * 4 + 0] = nvl.x; scal[nxt * 4 + 1] = nvl.y; }
-                    }
-                } else if (isY) {
-                    cf* a = Ys + (size_t)ifirst * LS + col;
-                    for (int i = ifirst; i < nv; i += 2, a += 2 * LS) *a = cf_fma(vb[i], tw, *a);
-                } else {
-                    cf* a = Zs + (size_t)ifirst * ZS + col;
-                    int i = ifirst;
-                    for (; i < zsplit; i += 2, a += 2 * ZS) *a = cf_fma(vb[i], tw, *a);
-                    cf* b = zg + (size_t)(i - nzs) * ZS + col;
-                    for (; i < nv; i += 2, b += 2 * ZS) *b = cf_fma(vb[i], tw, *b);
-                }
-            } else if (reflect && isY && col == j) {
-                for (int i = j + half; i < nv; i += 2) Ys[(size_t)i * LS + j] = (i == j) ? alpha : cf_make(0.f, 0.f);
-            } else if (!reflect && record) {
-                for (int i = j + 1 + half; i < nv; i += 2) {
-                    cf v = Ys[(size_t)i * LS + col];
-                    vn[i] = v;
-                    if (i > j + 1) t2 += cf_abs2(v);
-                    else { scal[nxt * 4 + 0] = v.x; scal[nxt * 4 + 1] = v.y; }
-                }
-            }
-            t2 += __shfl_xor_sync(0xffffffffu, t2, 1);
-            if (record && half == 0) scal[nxt * 4 + 2] = t2;
-            __syncthreads();
-        }
-    }
+    // ---- step 1: Householder QR, R only ------------------------------------------------------
+    if (P.do_qr) householder_forward<0>(Ys, LS, nv, L, min(nv - 1, L), vbuf, nvp, scal, nullptr);
 
-    // ---- phase 2: one-sided Jacobi on the rows of Y ------------------------------------------
+    // ---- step 2: one-sided Jacobi on the rows of Y -------------------------------------------
     const int nact = P.do_qr ? min(nv, L) : nv;    // rows >= L of R are exactly zero
     const int nb = 2 * ((nact + 7) / 8);           // 4-row blocks (even count)
     const int mcirc = nb - 1;
     const int ngroups = nb / 2;
     const int nrounds = nb > 2 ? nb - 1 : 1;
-    const int ylanes = P.LC / 32, zlanes = P.ZC / 32;
-    float4* rot = rotbuf + warp * NSLOT;
+    const int ylanes = P.LC / 32;
     int sweeps = 0, status = 0;
     if (nact >= 2) {
         status = 1;
         for (int sweep = 0; sweep < P.max_sweeps; ++sweep) {
-            int my_rot = 0;
+            // refresh the cached squared norms (they are updated by +-t|g| within the sweep)
+            for (int i = warp; i < 4 * nb; i += NW) {
+                const cf* yr = Ys + (size_t)i * LS;
+                float s2 = 0.f;
+#pragma unroll
+                for (int t = 0; t < EPL; ++t)
+                    if (t < ylanes) s2 += cf_abs2(yr[lane + 32 * t]);
+                s2 = warp_sum(s2);
+                if (lane == 0) nrm[i] = s2;
+            }
+            __syncthreads();
+            bool big = false;
             for (int r = 0; r < nrounds; ++r) {
                 for (int g = warp; g < ngroups; g += NW) {
                     int I, Jb;
                     if (nb == 2) { I = 0; Jb = 1; }
                     else if (g == 0) { I = mcirc; Jb = r; }
                     else { I = (r + g) % mcirc; Jb = (r - g + mcirc) % mcirc; }
-                    int rows[8];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { rows[i] = 4 * I + i; rows[4 + i] = 4 * Jb + i; }
-                    cf v[8][EPL];                  // first the Y rows, later re-used for the Z rows
+                    cf* rowA = Ys + (size_t)(4 * I) * LS + lane;
+                    cf* rowB = Ys + (size_t)(4 * Jb) * LS + lane;
+                    cf v[8][EPL];
                     float a[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const cf* yr = Ys + (size_t)rows[i] * LS;
-                        float s2 = 0.f;
+                    for (int i = 0; i < 4; ++i) {
 #pragma unroll
                         for (int t = 0; t < EPL; ++t) {
-                            v[i][t] = (t < ylanes) ? yr[lane + 32 * t] : cf_make(0.f, 0.f);
-                            s2 += cf_abs2(v[i][t]);
+                            v[i][t] = (t < ylanes) ? rowA[(size_t)i * LS + 32 * t] : cf_make(0.f, 0.f);
+                            v[4 + i][t] = (t < ylanes) ? rowB[(size_t)i * LS + 32 * t] : cf_make(0.f, 0.f);
                         }
-                        a[i] = s2;
+                        a[i] = nrm[4 * I + i];
+                        a[4 + i] = nrm[4 * Jb + i];
                     }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1)
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) a[i] += __shfl_xor_sync(0xffffffffu, a[i], o);
                     int nrot = 0;
-                    const bool intra = (r == 0);
-                    if (intra) {
-                        nrot += sub_round_y<0, 2, 4, 6, 1, 3, 5, 7>(v, a, P.tol2, rot, 0, lane);
-                        nrot += sub_round_y<0, 1, 4, 5, 2, 3, 6, 7>(v, a, P.tol2, rot, 4, lane);
-                        nrot += sub_round_y<0, 1, 4, 5, 3, 2, 7, 6>(v, a, P.tol2, rot, 8, lane);
+                    if (r == 0) {
+                        nrot += sub_round_y<0, 2, 4, 6, 1, 3, 5, 7>(v, a, P.tol2, lane, big);
+                        nrot += sub_round_y<0, 1, 4, 5, 2, 3, 6, 7>(v, a, P.tol2, lane, big);
+                        nrot += sub_round_y<0, 1, 4, 5, 3, 2, 7, 6>(v, a, P.tol2, lane, big);
                     }
-                    nrot += sub_round_y<0, 1, 2, 3, 4, 5, 6, 7>(v, a, P.tol2, rot, 12, lane);
-                    nrot += sub_round_y<0, 1, 2, 3, 5, 6, 7, 4>(v, a, P.tol2, rot, 16, lane);
-                    nrot += sub_round_y<0, 1, 2, 3, 6, 7, 4, 5>(v, a, P.tol2, rot, 20, lane);
-                    nrot += sub_round_y<0, 1, 2, 3, 7, 4, 5, 6>(v, a, P.tol2, rot, 24, lane);
+                    nrot += sub_round_y<0, 1, 2, 3, 4, 5, 6, 7>(v, a, P.tol2, lane, big);
+                    nrot += sub_round_y<0, 1, 2, 3, 5, 6, 7, 4>(v, a, P.tol2, lane, big);
+                    nrot += sub_round_y<0, 1, 2, 3, 6, 7, 4, 5>(v, a, P.tol2, lane, big);
+                    nrot += sub_round_y<0, 1, 2, 3, 7, 4, 5, 6>(v, a, P.tol2, lane, big);
                     if (nrot) {
 #pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            cf* yr = Ys + (size_t)rows[i] * LS;
+                        for (int i = 0; i < 4; ++i) {
 #pragma unroll
-                            for (int t = 0; t < EPL; ++t)
-                                if (t < ylanes) yr[lane + 32 * t] = v[i][t];
-                        }
-                        // Z phase: same registers, rotations replayed from the log
-                        __syncwarp();
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            const bool ok = rows[i] < nv;
-                            const cf* zr = ok ? zrow(rows[i]) : Ys;
-#pragma unroll
-                            for (int t = 0; t < EPL; ++t)
-                                v[i][t] = (ok && t < zlanes) ? zr[lane + 32 * t] : cf_make(0.f, 0.f);
-                        }
-                        if (intra) {
-                            sub_round_z<0, 2, 4, 6, 1, 3, 5, 7>(v, rot, 0);
-                            sub_round_z<0, 1, 4, 5, 2, 3, 6, 7>(v, rot, 4);
-                            sub_round_z<0, 1, 4, 5, 3, 2, 7, 6>(v, rot, 8);
-                        }
-                        sub_round_z<0, 1, 2, 3, 4, 5, 6, 7>(v, rot, 12);
-                        sub_round_z<0, 1, 2, 3, 5, 6, 7, 4>(v, rot, 16);
-                        sub_round_z<0, 1, 2, 3, 6, 7, 4, 5>(v, rot, 20);
-                        sub_round_z<0, 1, 2, 3, 7, 4, 5, 6>(v, rot, 24);
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) {
-                            if (rows[i] < nv) {
-                                cf* zr = zrow(rows[i]);
-#pragma unroll
-                                for (int t = 0; t < EPL; ++t)
-                                    if (t < zlanes) zr[lane + 32 * t] = v[i][t];
+                            for (int t = 0; t < EPL; ++t) {
+                                if (t < ylanes) {
+                                    rowA[(size_t)i * LS + 32 * t] = v[i][t];
+                                    rowB[(size_t)i * LS + 32 * t] = v[4 + i][t];
+                                }
                             }
                         }
-                        my_rot += nrot;
-                        __syncwarp();              // the log is rewritten by the next group step
+                        float am = a[0];
+#pragma unroll
+                        for (int i = 1; i < 8; ++i) if (lane == i) am = a[i];
+                        if (lane < 8) nrm[lane < 4 ? 4 * I + lane : 4 * Jb + lane - 4] = am;
                     }
                 }
                 __syncthreads();
             }
-            if (lane == 0 && my_rot) atomicAdd(&cnt[sweep & 1], my_rot);
-            __syncthreads();
-            int total = cnt[sweep & 1];
-            if (tid == 0) cnt[(sweep + 1) & 1] = 0;
             sweeps = sweep + 1;
-            if (total == 0) { status = 0; break; }
-            // the reset of the other counter is ordered before its next use by the barriers above
+            if (!__syncthreads_or(big ? 1 : 0)) { status = 0; break; }
         }
     }
 
-    // ---- phase 3: singular values, stable descending sort, split/absorb -----------------------
+    // ---- step 3: singular values, stable descending sort --------------------------------------
     __syncthreads();
     for (int i = warp; i < nvp; i += NW) {
         float s2 = 0.f;
@@ -455,7 +471,6 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
     if (myrank >= 0) perm[myrank] = tid;
     __syncthreads();
 
-    const int k = P.k;
     cf *left, *right; float* sv;
     if (P.descs) {
         int di = job / P.nbatch, bi = job % P.nbatch;
@@ -468,52 +483,153 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
         right = P.right + (size_t)job * P.right_stride;
         sv = P.svals ? P.svals + (size_t)job * P.svals_stride : nullptr;
     }
-    if (P.lc) {
-        // right [k][L] = Y_k ; left [nv][k] = conj(Z_k)^T
-        for (int e = tid; e < k * L; e += ST) { int j = e / L, c = e - j * L; right[e] = cf_scale(scale_out, Ys[(size_t)perm[j] * LS + c]); }
-        for (int e = tid; e < nv * k; e += ST) { int a_ = e / k, j = e - a_ * k; left[e] = cf_conj(zrow(perm[j])[a_]); }
-    } else {
-        // left [L][k] = Y_k^T ; right [k][nv] = conj(Z_k)
-        for (int e = tid; e < L * k; e += ST) { int a_ = e / k, j = e - a_ * k; left[e] = cf_scale(scale_out, Ys[(size_t)perm[j] * LS + a_]); }
-        for (int e = tid; e < k * nv; e += ST) { int j = e / nv, b_ = e - j * nv; right[e] = cf_conj(zrow(perm[j])[b_]); }
-    }
     if (sv) for (int j = tid; j < min(nv, L); j += ST) sv[j] = scale_out * sig[perm[j]];
     if (P.info && tid == 0) { P.info[2 * job] = status; P.info[2 * job + 1] = sweeps; }
+    if (k <= 0) return;
+
+    // ---- step 4: W = (s X) Y_k^H diag(1/sigma'^2)  (columns ~ u_j), then Q from its QR --------
+    // thread tile: rows a = lane + 32 i, columns j = warp + 16 jj
+    {
+        cf acc[4][8];
+        int pj[8];
+        float rinv[8];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int j = warp + NW * jj;
+            pj[jj] = j < k ? perm[j] : 0;
+            const float s = j < k ? sig[pj[jj]] : 0.f;
+            // sigma' below 1e-12 (max|x| is in [1,2)) is noise of noise: leave the column to the
+            // QR, which completes the basis with an arbitrary orthonormal vector (as LAPACK does)
+            rinv[jj] = s > 1e-12f ? 1.0f / s : 0.f;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[i][jj] = cf_make(0.f, 0.f);
+        }
+        const int njj = warp < k ? (k - warp + NW - 1) / NW : 0;
+        for (int c0 = 0; c0 < L; c0 += XCH) {
+            const int cw = min(XCH, L - c0);
+            for (int e = tid; e < 128 * XCH; e += ST) {
+                const int a_ = e / XCH, cc = e - a_ * XCH;
+                cf v = cf_make(0.f, 0.f);
+                if (a_ < nv && cc < cw) { v = X[(size_t)a_ * L + c0 + cc]; v.x *= scale_in; v.y *= scale_in; }
+                Xs[a_ * (XCH + 1) + cc] = v;
+            }
+            __syncthreads();
+            for (int cc = 0; cc < cw; ++cc) {
+                cf xa[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) xa[i] = Xs[(lane + 32 * i) * (XCH + 1) + cc];
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    if (jj < njj) {
+                        const cf yb = Ys[(size_t)pj[jj] * LS + c0 + cc];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[i][jj] = cf_fma_conja(yb, xa[i], acc[i][jj]);   // x conj(y)
+                    }
+                }
+            }
+            __syncthreads();
+        }
+        // all reads of Y are done (barrier above): overwrite it with W [nv][k]
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int j = warp + NW * jj;
+            if (j < k) {
+                const float r = rinv[jj];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int a_ = lane + 32 * i;
+                    if (a_ < nv) {
+                        cf w = acc[i][jj];
+                        w.x = (w.x * r) * r; w.y = (w.y * r) * r;
+                        Ys[(size_t)a_ * LS + j] = w;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    householder_forward<1>(Ys, LS, nv, k, k, vbuf, nvp, scal, tau_arr);
+    householder_form_q(Ys, LS, nv, k, vbuf, nvp, tau_arr);
+
+    // ---- step 5: P = Q^H X (k x L) and the outputs ---------------------------------------------
+    // thread tile: columns c = lane + 32 ci, rows j = warp + 16 jj
+    {
+        cf acc[8][4];
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj)
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) acc[jj][ci] = cf_make(0.f, 0.f);
+        const int njj = warp < k ? (k - warp + NW - 1) / NW : 0;
+        const int XLS = P.LC + 4;
+        for (int a0 = 0; a0 < nv; a0 += XCH) {
+            const int ah = min(XCH, nv - a0);
+            for (int e = tid; e < ah * P.LC; e += ST) {
+                const int al = e / P.LC, c = e - al * P.LC;
+                Xs[al * XLS + c] = c < L ? X[(size_t)(a0 + al) * L + c] : cf_make(0.f, 0.f);
+            }
+            __syncthreads();
+            for (int al = 0; al < ah; ++al) {
+                cf xb[4];
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) xb[ci] = (ci < ylanes) ? Xs[al * XLS + lane + 32 * ci] : cf_make(0.f, 0.f);
+                const cf* qrow = Ys + (size_t)(a0 + al) * LS + warp;
+#pragma unroll
+                for (int jj = 0; jj < 8; ++jj) {
+                    if (jj < njj) {
+                        const cf q = qrow[NW * jj];
+#pragma unroll
+                        for (int ci = 0; ci < 4; ++ci) acc[jj][ci] = cf_fma_conja(q, xb[ci], acc[jj][ci]);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+#pragma unroll
+        for (int jj = 0; jj < 8; ++jj) {
+            const int j = warp + NW * jj;
+            if (j < k) {
+#pragma unroll
+                for (int ci = 0; ci < 4; ++ci) {
+                    const int c = lane + 32 * ci;
+                    if (c < L) {
+                        if (P.lc) right[(size_t)j * L + c] = acc[jj][ci];      // S.Vh  [k][L]
+                        else left[(size_t)c * k + j] = acc[jj][ci];           // U.S   [L][k]
+                    }
+                }
+            }
+        }
+    }
+    if (P.lc) {
+        // left [nv][k] = Q
+        for (int e = tid; e < nv * k; e += ST) { int a_ = e / k, j = e - a_ * k; left[e] = Ys[(size_t)a_ * LS + j]; }
+    } else {
+        // right [k][nv] = Q^T
+        for (int e = tid; e < k * nv; e += ST) { int j = e / nv, b_ = e - j * nv; right[e] = Ys[(size_t)b_ * LS + j]; }
+    }
 }
 
-struct Layout { int nvp, LC, LS, ZC, ZS, nz_smem; size_t smem; };
+struct Layout { int nvp, LC, LS; size_t smem; };
 
 Layout make_layout(int nv, int L) {
     Layout lo;
     lo.nvp = (nv + 7) / 8 * 8;
-    lo.LC = (L + 31) / 32 * 32; lo.LS = lo.LC + 1;
-    lo.ZC = (nv + 31) / 32 * 32; lo.ZS = lo.ZC + 1;
-    size_t fixed = (size_t)NW * NSLOT * 16 + (size_t)lo.nvp * lo.LS * 8 + (size_t)2 * lo.nvp * 8 + (size_t)lo.nvp * 8 + NW * 4 + 2 * 4 + 64;
-    int dev = 0, optin = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || optin <= 0)
-        optin = 232448;      // sm_100: 227 KB (also the value assumed when planning without a device)
-    size_t avail = (size_t)optin > fixed ? (size_t)optin - fixed : 0;
-    size_t per_row = (size_t)lo.ZS * 8;
-    int fit = (int)(avail / per_row);
-    lo.nz_smem = fit >= nv ? nv : fit;
-    lo.smem = fixed + (size_t)lo.nz_smem * per_row;
+    lo.LC = (L + 31) / 32 * 32;
+    lo.LS = lo.LC + 4;           // rows 16-byte aligned; 4 consecutive rows x 4 columns hit 16 distinct 8-byte banks
+    lo.smem = ((size_t)lo.nvp * lo.LS + XS_ELEMS + 2 * (size_t)lo.nvp) * 8 + (size_t)lo.nvp * 16 + NW * 4 + 64;
     return lo;
 }
 
 }  // namespace
 
-size_t svd_small_global_z_elems(int nv, int L) {
-    Layout lo = make_layout(nv, L);
-    return (size_t)(nv - lo.nz_smem) * lo.ZS;
-}
+// (the Z spill of the first implementation is gone: nothing is needed in global memory)
+size_t svd_small_global_z_elems(int nv, int L) { (void)nv; (void)L; return 0; }
 
 int launch_svd_small(const cf* X, int64_t x_job_stride, int njobs, int nv, int L, int k,
                      int left_canonical, const mpsb_gate2_desc* descs, int ndesc, int nbatch,
                      cf* left, int64_t left_stride, cf* right, int64_t right_stride,
                      float* svals, int64_t svals_stride, int32_t* info, cf* zglobal,
                      cudaStream_t st) {
-    (void)ndesc;
+    (void)ndesc; (void)zglobal;
     if (njobs <= 0) return 0;
     MPSB_ARG(nv >= 1 && L >= 1 && nv <= MPSB_MAX_SMALL_DIM && L <= MPSB_MAX_SMALL_DIM,
              "svd_small: shape %d x %d outside [1, %d]", nv, L, MPSB_MAX_SMALL_DIM);
@@ -522,10 +638,7 @@ int launch_svd_small(const cf* X, int64_t x_job_stride, int njobs, int nv, int L
     SvdSmallParams P;
     P.X = X; P.x_stride = x_job_stride;
     P.nv = nv; P.L = L; P.k = k; P.lc = left_canonical;
-    P.nvp = lo.nvp; P.LS = lo.LS; P.ZS = lo.ZS; P.LC = lo.LC; P.ZC = lo.ZC;
-    P.nz_smem = lo.nz_smem;
-    P.zg = zglobal; P.zg_stride = (int64_t)(nv - lo.nz_smem) * lo.ZS;
-    MPSB_ARG(P.zg_stride == 0 || zglobal != nullptr, "svd_small: Z spill workspace missing");
+    P.nvp = lo.nvp; P.LS = lo.LS; P.LC = lo.LC;
     P.descs = descs; P.nbatch = nbatch > 0 ? nbatch : 1;
     P.left = left; P.left_stride = left_stride; P.right = right; P.right_stride = right_stride;
     P.svals = svals; P.svals_stride = svals_stride;

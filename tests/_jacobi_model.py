@@ -1,11 +1,13 @@
-"""CPU model (numpy, complex64) of the CUDA small-SVD kernel (mpsim_b200/csrc/svd_small.cuh):
-Householder QR preconditioning -> one-sided Jacobi on the rows of R with the block tournament
-schedule -> stable descending sort -> extraction of the isometry and the S-weighted factor.
+"""CPU model (numpy, complex64) of the CUDA small-SVD kernel (mpsim_b200/csrc/svd_small.cu):
+Householder QR preconditioning (R only) -> one-sided Jacobi on the rows of R with the block
+tournament schedule -> stable descending sort -> W = X V_k -> isometry Q from a Householder QR of
+W -> weighted factor Q^H X.
 
 It exists to validate schedule, formulas, tie-breaking and extraction on the CPU (tests/
 test_jacobi_model.py) before anything runs on a GPU; it is NOT used by the product.
 
-Invariant: Z @ M0 == Y at all times (Z unitary), so  M0 = Z^H Y  exactly, converged or not.
+Invariant: Q has orthonormal columns by construction, so Q (Q^H X) is an exact orthogonal
+projection of X, converged or not.
 """
 import numpy as np
 
@@ -55,7 +57,7 @@ def householder_qr(Y, Z, m):
         v = x.copy()
         v[0] = x0 - alpha
         tau = F(1.0) / F(normx * F(normx + ax0))      # 2 / ||v||^2
-        for A in (Y, Z):
+        for A in ((Y,) if Z is None else (Y, Z)):
             w = np.conj(v) @ A[j:m, :]
             A[j:m, :] -= np.outer(tau * v, w).astype(C)
         Y[j, j] = alpha
@@ -120,19 +122,19 @@ def rotate(Y, Z, p, q, tol2):
         return 0
     c, s = rotation_params(a, b, g)
     Y[p], Y[q] = apply_rotation(c, s, yp, yq)
-    Z[p], Z[q] = apply_rotation(c, s, Z[p].copy(), Z[q].copy())
+    if Z is not None:
+        Z[p], Z[q] = apply_rotation(c, s, Z[p].copy(), Z[q].copy())
     return 1
 
 
 def orthogonalize_rows(M, max_sweeps=30, tol=3e-6, qr=True):
-    """Returns Y, Z, sweeps, rotations with Z[:, :nv] @ M == Y and rows of Y orthogonal."""
+    """Returns Y, sweeps, rotations: rows of Y orthogonal, Y = (some unitary) @ M."""
     nv, L = M.shape
     nvp = max(8, (nv + 7) // 8 * 8)
     Y = np.zeros((nvp, L), C)
     Y[:nv] = M
-    Z = np.eye(nvp, dtype=C)
     if qr:
-        householder_qr(Y, Z, nv)
+        householder_qr(Y, None, nv)
     nact = min(nv, L) if qr else nv            # rows >= L of R are exactly zero
     nb = max(2, (nact + 7) // 8 * 2)
     rounds = block_rounds(nb)
@@ -145,11 +147,48 @@ def orthogonalize_rows(M, max_sweeps=30, tol=3e-6, qr=True):
                 rows = [4 * I + i for i in range(4)] + [4 * J + i for i in range(4)]
                 for sub in ((INTRA if r == 0 else []) + CROSS):
                     for (x, y) in sub:
-                        nrot += rotate(Y, Z, rows[x], rows[y], tol2)
+                        nrot += rotate(Y, None, rows[x], rows[y], tol2)
         total += nrot
         if nrot == 0:
             break
-    return Y, Z, sweep + 1, total
+    return Y, sweep + 1, total
+
+
+def householder_q(W):
+    """First k columns of the unitary of a Householder QR of W (nv x k): H_0 ... H_{k-1} [I_k; 0],
+    with the kernel's skip rules (no reflector for an already reduced or negligible column)."""
+    nv, k = W.shape
+    A = W.astype(C).copy()
+    refl = []
+    for j in range(k):
+        x = A[j:, j].copy()
+        tail2 = F((np.abs(x[1:]) ** 2).sum())
+        x0 = x[0]
+        ax0sq = F(F(x0.real) * F(x0.real) + F(x0.imag) * F(x0.imag))
+        if ax0sq < F(1e-30):
+            x0, ax0sq = C(0), F(0)
+        if not (tail2 > 0 and F(tail2 + ax0sq) > F(1e-30)):
+            refl.append(None)
+            continue
+        ax0 = F(np.sqrt(ax0sq))
+        normx = F(np.sqrt(F(tail2 + ax0sq)))
+        phase = C(x0 * F(F(1) / ax0)) if ax0 > 0 else C(1)
+        alpha = C(-phase * normx)
+        v = x.copy()
+        v[0] = x0 - alpha
+        tau = F(1.0) / F(normx * F(normx + ax0))
+        w = np.conj(v) @ A[j:, j + 1:]
+        A[j:, j + 1:] -= np.outer(tau * v, w).astype(C)
+        refl.append((v, tau))
+    Q = np.zeros((nv, k), C)
+    Q[:k, :k] = np.eye(k, dtype=C)
+    for j in range(k - 1, -1, -1):
+        if refl[j] is None:
+            continue
+        v, tau = refl[j]
+        w = np.conj(v) @ Q[j:, j:]
+        Q[j:, j:] -= np.outer(tau * v, w).astype(C)
+    return Q
 
 
 def split(M, k, left_canonical=True, **kw):
@@ -157,15 +196,21 @@ def split(M, k, left_canonical=True, **kw):
     left_canonical:      left = U,    right = S Vh   (vectors = rows of M)
     not left_canonical:  left = U S,  right = Vh     (vectors = columns of M)."""
     m, n = M.shape
-    X = M if left_canonical else np.ascontiguousarray(M.T)
+    X = (M if left_canonical else np.ascontiguousarray(M.T)).astype(C)
     nv = X.shape[0]
-    Y, Z, sweeps, _ = orthogonalize_rows(X.astype(C), **kw)
+    mx = float(np.abs(np.concatenate([X.real.ravel(), X.imag.ravel()])).max()) if X.size else 0.0
+    scale = F(2.0 ** (1 - np.frexp(mx)[1])) if mx > 0 else F(1)       # max|x| -> [1, 2)
+    Xs = (X * scale).astype(C)
+    Y, sweeps, _ = orthogonalize_rows(Xs, **kw)
     norms = np.sqrt((np.abs(Y) ** 2).sum(axis=1, dtype=F)).astype(F)
     norms[nv:] = -1                           # padding rows sort last
     perm = np.argsort(-norms, kind="stable")
-    iso = np.conj(Z[perm[:k], :nv])           # k x nv
-    wgt = Y[perm[:k], :]                      # k x L
-    sig = norms[perm][:min(m, n)]
+    sk = norms[perm[:k]]
+    rinv = np.where(sk > F(1e-12), F(1) / np.maximum(sk, F(1e-30)), F(0)).astype(F)
+    W = ((Xs @ np.conj(Y[perm[:k]]).T).astype(C) * rinv * rinv).astype(C)      # nv x k, columns ~ u_j
+    Q = householder_q(W)
+    wgt = (np.conj(Q).T @ X).astype(C)        # k x L
+    sig = (norms[perm][:min(m, n)] / scale).astype(F)
     if left_canonical:
-        return iso.T.copy(), wgt, sig, sweeps       # U = Z_k^H ; S Vh = Y_k
-    return wgt.T.copy(), iso, sig, sweeps           # U S = Y_k^T ; Vh = conj(Z_k)
+        return Q, wgt, sig, sweeps                  # U = Q ; S Vh = Q^H X
+    return wgt.T.copy(), Q.T.copy(), sig, sweeps    # U S = (Q^H X)^T ; Vh = Q^T
