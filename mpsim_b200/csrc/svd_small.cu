@@ -40,6 +40,11 @@ constexpr int XCH = 32;          // staging chunk of X: columns in step 4, rows 
 constexpr int XS_ELEMS = 128 * (XCH + 1);   // >= XCH * (128 + 4)
 constexpr float BIG2 = 1e-4f * 1e-4f;       // a sweep without a rotation above this is the last
 
+// phase boundaries of CTA 0 (clock64), read back by mpsb_debug_phase_clocks: a profiling aid
+__device__ long long g_phase_clk[16];
+__device__ int g_dbg_flags;      // timing experiments only (set through mpsb_debug_set_flags)
+#define PHASE_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_clk[i] = clock64(); } while (0)
+
 struct SvdSmallParams {
     const cf* X; int64_t x_stride;
     int nv, L, k, lc;
@@ -173,38 +178,136 @@ __device__ __forceinline__ cf group_sum(cf w, int tpc) {
     return w;
 }
 
-// Householder reduction of A [nrows][ncols] (row stride LS), steps j = 0..nsteps-1, one barrier per
-// step: the threads of column j+1 record the next reflector while they update their column.
-//   STORE = 0 : A <- R (alpha on the diagonal, zeros below); reflectors are dropped.
-//   STORE = 1 : column j, rows j.. keep the reflector v_j (v_j[0] on the diagonal), tau[j] its
-//               scale (0 = identity): H_j = I - tau v v^H.
-// tpc threads share a column (rows interleaved).  vbuf [2][nvp], scal [8].
-template <int STORE>
-__device__ void householder_forward(cf* A, int LS, int nrows, int ncols, int nsteps, cf* vbuf, int nvp,
-                                    float* scal, float* tau_arr) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (nsteps <= 0) return;
-    const int tpc = threads_per_col(ncols);
-    if (warp == 0) {
-        float t2 = 0.f;
-        for (int i = lane; i < nrows; i += 32) {
-            cf v = A[(size_t)i * LS];
-            vbuf[i] = v;
-            if (i > 0) t2 += cf_abs2(v);
-        }
-        t2 = warp_sum(t2);
-        if (lane == 0) { cf x0 = A[0]; scal[0] = x0.x; scal[1] = x0.y; scal[2] = t2; }
+// Householder reduction of A [nrows][ncols] (row stride LS), register resident: tpc threads share
+// a column (thread (col, sub) keeps rows sub, sub + tpc, ... of its column in registers for the
+// whole factorisation), so a step only moves one column through shared memory (the first
+// implementation streamed the matrix through shared memory twice per step).
+// Step j:  every warp reads the published column j (zero above and on the diagonal; x0 aside),
+// reduces its norm and derives (v0, tau) redundantly -- no single warp is on the critical path and
+// one barrier per step suffices; the columns > j are updated in registers over warp-uniform chunks
+// of 8 register slots (the zeros of the published column make per-lane predicates unnecessary,
+// only the chunk holding row j patches in v0); the owners of column j+1 publish it.
+//   MODE 0 : A <- R (alpha on the diagonal, zeros below); the reflectors are dropped.
+//   MODE 1 : A <- Q = H_0 H_1 ... H_{k-1} [I_k; 0], the first k = ncols columns of the unitary
+//            (forward pass keeps v_j in column j, the backward pass forms Q in the same registers).
+// H_j = I - tau_j v_j v_j^H.  Shared memory: vbuf [2][VB], scal [8], tau_arr / v0_arr [>= ncols].
+constexpr int RMAX = 32;         // register slots per thread: nrows <= 128 with tpc >= 4
+constexpr int RCH = 8;           // slots per chunk
+constexpr int VB = 256;          // > 31 + 32 * 7: every slot of every chunk maps inside the buffer
+
+#define HH_CHUNKS(C0, C1, BODY)                                        \
+    _Pragma("unroll") for (int c_ = 0; c_ < RMAX / RCH; ++c_) {        \
+        if (c_ >= (C0) && c_ < (C1)) {                                 \
+            _Pragma("unroll") for (int u_ = 0; u_ < RCH; ++u_) {       \
+                const int t = c_ * RCH + u_;                           \
+                BODY                                                   \
+            }                                                          \
+        }                                                              \
     }
-    __syncthreads();
+// chunk CD carries the diagonal row (BODY_D), the chunks after it are plain (BODY)
+#define HH_CHUNKS_D(CD, C1, BODY_D, BODY)                              \
+    _Pragma("unroll") for (int c_ = 0; c_ < RMAX / RCH; ++c_) {        \
+        if (c_ == (CD)) {                                              \
+            _Pragma("unroll") for (int u_ = 0; u_ < RCH; ++u_) {       \
+                const int t = c_ * RCH + u_;                           \
+                BODY_D                                                 \
+            }                                                          \
+        } else if (c_ > (CD) && c_ < (C1)) {                           \
+            _Pragma("unroll") for (int u_ = 0; u_ < RCH; ++u_) {       \
+                const int t = c_ * RCH + u_;                           \
+                BODY                                                   \
+            }                                                          \
+        }                                                              \
+    }
+
+template <int MODE>
+__device__ __noinline__ void householder(cf* A, int LS, int nrows, int ncols, int nsteps, cf* vbuf, float* scal,
+                                         float* tau_arr, cf* v0_arr) {
+    const int tid = threadIdx.x, lane = tid & 31;
+    if (nsteps <= 0 && MODE == 0) return;
+    const int tpc = threads_per_col(ncols);
     const int col = tid / tpc, sub = tid % tpc;
     const bool mine = col < ncols;
+    const int c1 = ((nrows + tpc - 1) / tpc + RCH - 1) / RCH;        // chunks in use (warp-uniform)
+    const unsigned gmask = tpc == 32 ? 0xffffffffu : (((1u << tpc) - 1u) << (lane & ~(tpc - 1)));
+    cf a[RMAX];
+#pragma unroll
+    for (int t = 0; t < RMAX; ++t) {
+        const int row = sub + tpc * t;
+        a[t] = (mine && row < nrows) ? A[(size_t)row * LS + col] : cf_make(0.f, 0.f);
+    }
+    for (int i = tid; i < 2 * VB; i += ST) vbuf[i] = cf_make(0.f, 0.f);
+    __syncthreads();
+
+    // the tpc owners of column jn publish it: zeros down to and including row jn, x0 aside
+    auto publish = [&](int jn, cf* vn, float* sc) {
+        const int cj = jn / (RCH * tpc);
+        HH_CHUNKS(cj > 0 ? cj - 1 : 0, c1, {
+            const int row = sub + tpc * t;
+            vn[tpc * t] = row > jn ? a[t] : cf_make(0.f, 0.f);
+            if (row == jn) { sc[0] = a[t].x; sc[1] = a[t].y; }
+        })
+    };
+    // w = v^H a over my rows, reduced over the column's threads; then a -= tau v w.
+    // Each chunk's 8 reflector entries are loaded into registers first so that the shared-memory
+    // latency is paid once per chunk, not once per row.
+    auto reflect_column = [&](const cf* vb, int j, cf v0, float tau) {
+        const int cd = j / (RCH * tpc);
+        cf w0 = cf_make(0.f, 0.f), w1 = cf_make(0.f, 0.f);
+#pragma unroll
+        for (int c_ = 0; c_ < RMAX / RCH; ++c_) {
+            if (c_ >= cd && c_ < c1) {
+                cf vv[RCH];
+#pragma unroll
+                for (int u_ = 0; u_ < RCH; ++u_) vv[u_] = vb[tpc * (c_ * RCH + u_)];
+                if (c_ == cd) {
+#pragma unroll
+                    for (int u_ = 0; u_ < RCH; ++u_) if (sub + tpc * (c_ * RCH + u_) == j) vv[u_] = v0;
+                }
+#pragma unroll
+                for (int u_ = 0; u_ < RCH; ++u_) {
+                    if (u_ & 1) w1 = cf_fma_conja(vv[u_], a[c_ * RCH + u_], w1);
+                    else w0 = cf_fma_conja(vv[u_], a[c_ * RCH + u_], w0);
+                }
+            }
+        }
+        cf w = cf_add(w0, w1);
+        for (int o = tpc >> 1; o > 0; o >>= 1) {
+            w.x += __shfl_xor_sync(gmask, w.x, o);
+            w.y += __shfl_xor_sync(gmask, w.y, o);
+        }
+        const cf tw = cf_scale(-tau, w);
+#pragma unroll
+        for (int c_ = 0; c_ < RMAX / RCH; ++c_) {
+            if (c_ >= cd && c_ < c1) {
+                cf vv[RCH];
+#pragma unroll
+                for (int u_ = 0; u_ < RCH; ++u_) vv[u_] = vb[tpc * (c_ * RCH + u_)];
+                if (c_ == cd) {
+#pragma unroll
+                    for (int u_ = 0; u_ < RCH; ++u_) if (sub + tpc * (c_ * RCH + u_) == j) vv[u_] = v0;
+                }
+#pragma unroll
+                for (int u_ = 0; u_ < RCH; ++u_) a[c_ * RCH + u_] = cf_fma(vv[u_], tw, a[c_ * RCH + u_]);
+            }
+        }
+    };
+
+    if (mine && col == 0 && nsteps > 0) publish(0, vbuf + sub, scal);
+    __syncthreads();
+    cf my_alpha = cf_make(0.f, 0.f), my_v0 = cf_make(0.f, 0.f);
+    bool my_reflect = false;
+    const int dbg = g_dbg_flags;
     for (int j = 0; j < nsteps; ++j) {
         const int cur = j & 1, nxt = cur ^ 1;
-        const cf* vb = vbuf + cur * nvp;
-        cf* vn = vbuf + nxt * nvp;
+        const cf* vbl = vbuf + cur * VB;
+        float tail2 = 0.f;
+        if (!(dbg & 4)) {
+#pragma unroll
+            for (int m = 0; m < 4; ++m) tail2 += cf_abs2(vbl[lane + 32 * m]);
+            tail2 = warp_sum(tail2);
+        } else tail2 = 1.0f;
         cf x0 = cf_make(scal[cur * 4 + 0], scal[cur * 4 + 1]);
-        const float tail2 = scal[cur * 4 + 2];
-        const bool record = mine && (col == j + 1) && (j + 1 < nsteps);
         float ax0sq = cf_abs2(x0);
         // |x0|^2 below ~1e-30 is a denormal-range number with few significant bits: the
         // phase x0/|x0| would be off by 1e-4 and the reflector no longer unitary (seen on
@@ -215,113 +318,60 @@ __device__ void householder_forward(cf* A, int LS, int nrows, int ncols, int nst
         const bool reflect = tail2 > 0.f && tail2 + ax0sq > 1e-30f;
         cf v0 = cf_make(0.f, 0.f), alpha = cf_make(0.f, 0.f);
         float tau = 0.f;
-        if (reflect) {
+        if (reflect && !(dbg & 8)) {
             float ax0 = sqrtf(ax0sq);
             float normx = sqrtf(tail2 + ax0sq);
             cf ph = ax0 > 0.f ? cf_scale(1.0f / ax0, x0) : cf_make(1.f, 0.f);
             alpha = cf_scale(-normx, ph);
             v0 = cf_sub(x0, alpha);
             tau = 1.0f / (normx * (normx + ax0));
-        }
-        const bool upd = reflect && mine && col > j;
-        const int ifirst = j + sub + (sub == 0 ? tpc : 0);      // first of my rows handled with vb[]
-        cf* acol = A + col;
-        // pass 1: w = v^H A[:, col]
-        cf w = cf_make(0.f, 0.f);
-        if (upd) {
-            if (sub == 0) w = cf_fma_conja(v0, acol[(size_t)j * LS], w);
-            const cf* a = acol + (size_t)ifirst * LS;
-            for (int i = ifirst; i < nrows; i += tpc, a += (size_t)tpc * LS) w = cf_fma_conja(vb[i], *a, w);
-        }
-        w = group_sum(w, tpc);
-        // pass 2: A[:, col] -= tau v w
-        float t2 = 0.f;
-        if (upd) {
-            const cf tw = cf_scale(-tau, w);
-            if (sub == 0) acol[(size_t)j * LS] = cf_fma(v0, tw, acol[(size_t)j * LS]);
-            cf* a = acol + (size_t)ifirst * LS;
-            if (record) {
-                for (int i = ifirst; i < nrows; i += tpc, a += (size_t)tpc * LS) {
-                    cf nvl = cf_fma(vb[i], tw, *a);
-                    *a = nvl;
-                    vn[i] = nvl;
-                    if (i > j + 1) t2 += cf_abs2(nvl);
-                    else { scal[nxt * 4 + 0] = nvl.x; scal[nxt * 4 + 1] = nvl.y; }
-                }
-            } else {
-                for (int i = ifirst; i < nrows; i += tpc, a += (size_t)tpc * LS) *a = cf_fma(vb[i], tw, *a);
-            }
-        } else if (record) {                       // no reflector in this step: column j+1 as it is
-            for (int i = j + 1 + sub; i < nrows; i += tpc) {
-                cf v = acol[(size_t)i * LS];
-                vn[i] = v;
-                if (i > j + 1) t2 += cf_abs2(v);
-                else { scal[nxt * 4 + 0] = v.x; scal[nxt * 4 + 1] = v.y; }
-            }
-        } else if (mine && col == j) {
-            if (STORE) {
-                if (sub == 0) {
-                    tau_arr[j] = reflect ? tau : 0.f;
-                    if (reflect) acol[(size_t)j * LS] = v0;
-                }
-            } else if (reflect) {
-                for (int i = j + sub; i < nrows; i += tpc) acol[(size_t)i * LS] = (i == j) ? alpha : cf_make(0.f, 0.f);
-            }
-        }
-        {
-            cf t = group_sum(cf_make(t2, 0.f), tpc);
-            if (record && sub == 0) scal[nxt * 4 + 2] = t.x;
+        } else if (reflect) { v0 = x0; tau = 0.5f; }
+        if (MODE == 1 && tid == 0) { tau_arr[j] = tau; v0_arr[j] = v0; }
+        if (mine && col == j) { my_alpha = alpha; my_v0 = v0; my_reflect = reflect; }
+        if (mine && col > j) {
+            if (reflect && !(dbg & 1)) reflect_column(vbl + sub, j, v0, tau);
+            if (col == j + 1 && j + 1 < nsteps && !(dbg & 2)) publish(j + 1, vbuf + nxt * VB + sub, scal + nxt * 4);
         }
         __syncthreads();
     }
-}
-
-// A [nrows][k] holds the reflectors of householder_forward<1>; overwrite it with
-// Q = H_0 H_1 ... H_{k-1} [I_k; 0] (the unitary's first k columns), one barrier per step.
-__device__ void householder_form_q(cf* A, int LS, int nrows, int k, cf* vbuf, int nvp, const float* tau_arr) {
-    const int tid = threadIdx.x;
-    if (k <= 0) return;
-    const int tpc = threads_per_col(k);
-    const int col = tid / tpc, sub = tid % tpc;
-    const bool mine = col < k;
-    {
-        const int j = k - 1;
-        cf* vn = vbuf + (j & 1) * nvp;
-        for (int i = j + tid; i < nrows; i += ST) vn[i] = A[(size_t)i * LS + j];
+    if (MODE == 1) {
+        // backward: Q <- H_j Q for j = k-1 .. 0, in the same registers
+        const int k = ncols;
+        if (mine && col == k - 1) publish(k - 1, vbuf + ((k - 1) & 1) * VB + sub, scal);
+        __syncthreads();
+        for (int j = k - 1; j >= 0; --j) {
+            const float tau = tau_arr[j];
+            const cf v0 = v0_arr[j];
+            if (mine && col > j) {
+                if (tau != 0.f) reflect_column(vbuf + (j & 1) * VB + sub, j, v0, tau);
+            } else if (mine && col == j) {
+                // H_j e_j = e_j - tau conj(v_j[0]) v_j ; rows above j still hold R from the forward pass
+                const cf f = (tau != 0.f) ? cf_scale(-tau, cf_conj(v0)) : cf_make(0.f, 0.f);
+                HH_CHUNKS(0, c1, {
+                    const int row = sub + tpc * t;
+                    cf q = cf_make(0.f, 0.f);
+                    if (row >= j && row < nrows) {
+                        q = cf_mul(f, row == j ? v0 : a[t]);
+                        if (row == j) q.x += 1.0f;
+                    }
+                    a[t] = q;
+                })
+            } else if (mine && j > 0 && col == j - 1) {
+                publish(j - 1, vbuf + ((j - 1) & 1) * VB + sub, scal);
+            }
+            __syncthreads();
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < RMAX; ++t) {
+        const int row = sub + tpc * t;
+        if (mine && row < nrows) {
+            cf v = a[t];
+            if (MODE == 0 && my_reflect && row >= col) v = (row == col) ? my_alpha : cf_make(0.f, 0.f);
+            A[(size_t)row * LS + col] = v;
+        }
     }
     __syncthreads();
-    for (int j = k - 1; j >= 0; --j) {
-        const cf* vb = vbuf + (j & 1) * nvp;
-        cf* vn = vbuf + ((j & 1) ^ 1) * nvp;
-        const float tau = tau_arr[j];
-        cf* acol = A + col;
-        cf w = cf_make(0.f, 0.f);
-        const bool upd = mine && col > j && tau != 0.f;
-        if (upd) {
-            const cf* a = acol + (size_t)(j + sub) * LS;
-            for (int i = j + sub; i < nrows; i += tpc, a += (size_t)tpc * LS) w = cf_fma_conja(vb[i], *a, w);
-        }
-        w = group_sum(w, tpc);
-        if (upd) {
-            const cf tw = cf_scale(-tau, w);
-            cf* a = acol + (size_t)(j + sub) * LS;
-            for (int i = j + sub; i < nrows; i += tpc, a += (size_t)tpc * LS) *a = cf_fma(vb[i], tw, *a);
-        } else if (mine && col == j) {
-            // H_j e_j = e_j - tau conj(v_j[0]) v_j ; rows above j still hold R from the forward pass
-            const cf f = (tau != 0.f) ? cf_scale(-tau, cf_conj(vb[j])) : cf_make(0.f, 0.f);
-            for (int i = sub; i < nrows; i += tpc) {
-                cf q = cf_make(0.f, 0.f);
-                if (i >= j) {
-                    if (tau != 0.f) q = cf_mul(f, vb[i]);
-                    if (i == j) q.x += 1.0f;
-                }
-                acol[(size_t)i * LS] = q;
-            }
-        } else if (mine && j > 0 && col == j - 1) {
-            for (int i = j - 1 + sub; i < nrows; i += tpc) vn[i] = acol[(size_t)i * LS];
-        }
-        __syncthreads();
-    }
 }
 
 __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
@@ -332,13 +382,15 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
 
     cf* Ys = (cf*)smem_raw;                        // [nvp][LS]   Y, later W / Q
     cf* Xs = Ys + (size_t)nvp * LS;                // [XS_ELEMS]  staging of X for steps 4, 5
-    cf* vbuf = Xs + XS_ELEMS;                      // [2][nvp]
-    float* sig = (float*)(vbuf + 2 * nvp);         // [nvp]  sigma (scaled units)
+    cf* vbuf = Xs + XS_ELEMS;                      // [2][VB]
+    cf* v0_arr = vbuf + 2 * VB;                    // [nvp]
+    float* sig = (float*)(v0_arr + nvp);           // [nvp]  sigma (scaled units)
     float* nrm = sig + nvp;                        // [nvp]  cached squared row norms
     float* tau_arr = nrm + nvp;                    // [nvp]
     int* perm = (int*)(tau_arr + nvp);             // [nvp]
     float* scal = (float*)(perm + nvp);            // [NW]  (also the QR scalars: 8 used)
 
+    PHASE_MARK(0);
     // ---- step 0: load X scaled by an exact power of two so that max|x| is in [1, 2) ----------
     // (the guards below are absolute, and products of numerical zeros would otherwise
     //  underflow in the Gram entries; LAPACK scales for the same reason)
@@ -365,9 +417,11 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
     }
     __syncthreads();
 
+    PHASE_MARK(1);
     // ---- step 1: Householder QR, R only ------------------------------------------------------
-    if (P.do_qr) householder_forward<0>(Ys, LS, nv, L, min(nv - 1, L), vbuf, nvp, scal, nullptr);
+    if (P.do_qr) householder<0>(Ys, LS, nv, L, min(nv - 1, L), vbuf, scal, nullptr, nullptr);
 
+    PHASE_MARK(2);
     // ---- step 2: one-sided Jacobi on the rows of Y -------------------------------------------
     const int nact = P.do_qr ? min(nv, L) : nv;    // rows >= L of R are exactly zero
     const int nb = 2 * ((nact + 7) / 8);           // 4-row blocks (even count)
@@ -391,6 +445,8 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
             }
             __syncthreads();
             bool big = false;
+            // (per-block round counters instead of the block-wide barrier were tried and were
+            //  3x slower: the polling warps take issue slots from the ones they wait for)
             for (int r = 0; r < nrounds; ++r) {
                 for (int g = warp; g < ngroups; g += NW) {
                     int I, Jb;
@@ -445,6 +501,7 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
         }
     }
 
+    PHASE_MARK(3);
     // ---- step 3: singular values, stable descending sort --------------------------------------
     __syncthreads();
     for (int i = warp; i < nvp; i += NW) {
@@ -487,6 +544,7 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
     if (P.info && tid == 0) { P.info[2 * job] = status; P.info[2 * job + 1] = sweeps; }
     if (k <= 0) return;
 
+    PHASE_MARK(4);
     // ---- step 4: W = (s X) Y_k^H diag(1/sigma'^2)  (columns ~ u_j), then Q from its QR --------
     // thread tile: rows a = lane + 32 i, columns j = warp + 16 jj
     {
@@ -548,8 +606,9 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
         }
         __syncthreads();
     }
-    householder_forward<1>(Ys, LS, nv, k, k, vbuf, nvp, scal, tau_arr);
-    householder_form_q(Ys, LS, nv, k, vbuf, nvp, tau_arr);
+    PHASE_MARK(5);
+    householder<1>(Ys, LS, nv, k, k, vbuf, scal, tau_arr, v0_arr);
+    PHASE_MARK(6);
 
     // ---- step 5: P = Q^H X (k x L) and the outputs ---------------------------------------------
     // thread tile: columns c = lane + 32 ci, rows j = warp + 16 jj
@@ -599,6 +658,7 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
             }
         }
     }
+    PHASE_MARK(7);
     if (P.lc) {
         // left [nv][k] = Q
         for (int e = tid; e < nv * k; e += ST) { int a_ = e / k, j = e - a_ * k; left[e] = Ys[(size_t)a_ * LS + j]; }
@@ -606,6 +666,7 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
         // right [k][nv] = Q^T
         for (int e = tid; e < k * nv; e += ST) { int j = e / nv, b_ = e - j * nv; right[e] = Ys[(size_t)b_ * LS + j]; }
     }
+    PHASE_MARK(8);
 }
 
 struct Layout { int nvp, LC, LS; size_t smem; };
@@ -615,11 +676,19 @@ Layout make_layout(int nv, int L) {
     lo.nvp = (nv + 7) / 8 * 8;
     lo.LC = (L + 31) / 32 * 32;
     lo.LS = lo.LC + 4;           // rows 16-byte aligned; 4 consecutive rows x 4 columns hit 16 distinct 8-byte banks
-    lo.smem = ((size_t)lo.nvp * lo.LS + XS_ELEMS + 2 * (size_t)lo.nvp) * 8 + (size_t)lo.nvp * 16 + NW * 4 + 64;
+    lo.smem = ((size_t)lo.nvp * lo.LS + XS_ELEMS + 2 * (size_t)VB + lo.nvp) * 8 + (size_t)lo.nvp * 16 + NW * 4 + 64;
     return lo;
 }
 
 }  // namespace
+
+extern "C" int mpsb_debug_set_flags(int flags) {
+    return (int)cudaMemcpyToSymbol(g_dbg_flags, &flags, sizeof(int));
+}
+
+extern "C" int mpsb_debug_phase_clocks(long long* out16) {
+    return (int)cudaMemcpyFromSymbol(out16, g_phase_clk, sizeof(long long) * 16);
+}
 
 // (the Z spill of the first implementation is gone: nothing is needed in global memory)
 size_t svd_small_global_z_elems(int nv, int L) { (void)nv; (void)L; return 0; }

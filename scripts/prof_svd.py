@@ -9,6 +9,9 @@ njobs = int(sys.argv[1]) if len(sys.argv) > 1 else 148
 m = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 lib = _lib.load(require_device=True)
+import os
+if os.environ.get('DBG'):
+    lib.mpsb_debug_set_flags(int(os.environ['DBG']))
 rng = np.random.default_rng(0)
 a = rng.standard_normal((njobs, m, m)) + 1j * rng.standard_normal((njobs, m, m))
 u, s, vh = np.linalg.svd(a)
@@ -29,3 +32,10 @@ for _ in range(reps):
     e1.record()
     torch.cuda.synchronize()
     print("ms", e0.elapsed_time(e1), "sweeps", info[:, 1].float().mean().item(), "status", int(info[:, 0].sum()))
+
+import ctypes
+clk = (ctypes.c_longlong * 16)()
+if hasattr(lib, "mpsb_debug_phase_clocks") and lib.mpsb_debug_phase_clocks(clk) == 0:
+    names = ["load", "qr1", "jacobi", "sort", "W=XV", "qr2+formQ", "P=QhX", "write"]
+    c = list(clk)
+    print("phase cycles (CTA 0):", {n: c[i + 1] - c[i] for i, n in enumerate(names)}, "total", c[8] - c[0])
