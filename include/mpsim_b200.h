@@ -109,7 +109,15 @@ int mpsb_amplitudes(const mpsb_site_ref* sites_dev, int nsites, int nbatch, int 
 int mpsb_cgemm(const void* A, int64_t a_rs, int64_t a_cs, int conj_a, int64_t a_bs,
                const void* B, int64_t b_rs, int64_t b_cs, int conj_b, int64_t b_bs,
                void* C, int64_t c_ld, int64_t c_bs, int M, int N, int K, int nbatch, void* stream);
-/* theta matrix only: out[job] = row-major [d*chiL][d*chiR] with rows (l,o1), cols (o2,r). */
+/* Same product on the tensor cores (tcgen05 3xTF32, tc_gemm.cu): dense row-major A [M][K],
+ * B [K][N], C [M][N] (row stride c_ld), batch strides in elements. */
+size_t mpsb_cgemm_tc_workspace_bytes(int M, int N, int K, int nbatch);
+int mpsb_cgemm_tc(const void* A, int64_t a_bs, const void* B, int64_t b_bs, void* C, int64_t c_ld, int64_t c_bs,
+                  int M, int N, int K, int nbatch, void* workspace, size_t workspace_bytes, void* stream);
+/* theta matrix only: out[job] = row-major [d*chiL][d*chiR] with rows (l,o1), cols (o2,r).
+ * With a workspace of mpsb_theta_workspace_bytes() the tensor-core kernel is used where it
+ * applies (d = 2, chi >= 32); without one the FFMA kernel. */
+size_t mpsb_theta_workspace_bytes(int ndesc, int nbatch, int d, int chiL, int chiM, int chiR);
 int mpsb_theta(const mpsb_gate2_desc* descs_dev, int ndesc, int nbatch, int d,
                int chiL, int chiM, int chiR, void* out, void* workspace, size_t workspace_bytes,
                void* stream);

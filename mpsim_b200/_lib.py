@@ -47,6 +47,10 @@ SYMBOLS = {
     "mpsb_amplitudes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),
     "mpsb_cgemm": (c_int, [c_void_p, c_int64, c_int64, c_int, c_int64, c_void_p, c_int64, c_int64, c_int, c_int64,
                            c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int, c_void_p]),
+    "mpsb_cgemm_tc_workspace_bytes": (c_size_t, [c_int] * 4),
+    "mpsb_cgemm_tc": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_int, c_int,
+                              c_void_p, c_size_t, c_void_p]),
+    "mpsb_theta_workspace_bytes": (c_size_t, [c_int] * 6),
     "mpsb_theta": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mpsb_svd_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "mpsb_svd": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,

@@ -1,5 +1,6 @@
 // extern "C" surface of libmpsim_b200 (see include/mpsim_b200.h for the contract).
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 
@@ -53,6 +54,13 @@ struct Gate2Plan {
     size_t x_elems, extra_elems, job_elems;
 };
 
+// theta runs on the tensor cores (tc_gemm.cu) for qubits once the tile is reasonably filled;
+// MPSB_THETA_TC=0/1 forces the choice (debugging / A-B timing)
+bool theta_uses_tc(int d, int chiL, int chiM, int chiR) {
+    if (const char* e = getenv("MPSB_THETA_TC")) return atoi(e) != 0 && d == 2;
+    return d == 2 && chiL >= 32 && chiR >= 32 && chiM >= 16;
+}
+
 Gate2Plan plan_gate2(int d, int chiL, int chiR, int lc) {
     Gate2Plan p;
     p.m = d * chiL; p.n = d * chiR;
@@ -87,7 +95,8 @@ size_t mpsb_gate2_workspace_bytes(int ndesc, int nbatch, int d, int chiL, int ch
     if (ndesc <= 0 || nbatch <= 0 || chiL <= 0 || chiR <= 0) return 0;
     // worst of the two orientations so one workspace serves both canonical forms
     size_t a = plan_gate2(d, chiL, chiR, 1).job_elems, b = plan_gate2(d, chiL, chiR, 0).job_elems;
-    return (a > b ? a : b) * sizeof(cf) * (size_t)ndesc * nbatch + 256;
+    size_t tc = d == 2 ? align_up(tc_theta_workspace_floats(ndesc * nbatch, chiL, chiM, chiR) * sizeof(float), 256) : 0;
+    return (a > b ? a : b) * sizeof(cf) * (size_t)ndesc * nbatch + 256 + tc;
 }
 
 int mpsb_apply_gate2(const mpsb_gate2_desc* descs_dev, int ndesc, int nbatch,
@@ -106,13 +115,20 @@ int mpsb_apply_gate2(const mpsb_gate2_desc* descs_dev, int ndesc, int nbatch,
     MPSB_ARG(k >= 0 && k <= mn, "apply_gate2: k=%d outside [0, %d]", k, mn);
     MPSB_ARG(njobs <= 65535, "apply_gate2: %d applications in one call (max 65535); split the call", njobs);
     Gate2Plan p = plan_gate2(d, chiL, chiR, left_canonical ? 1 : 0);
-    size_t need = p.job_elems * sizeof(cf) * (size_t)njobs;
+    const bool tc = theta_uses_tc(d, chiL, chiM, chiR);
+    size_t need_svd = align_up(p.job_elems * sizeof(cf) * (size_t)njobs, 256);
+    size_t need = need_svd + (tc ? tc_theta_workspace_floats(njobs, chiL, chiM, chiR) * sizeof(float) : 0);
     MPSB_ARG(workspace != nullptr && workspace_bytes >= need, "apply_gate2: workspace %zu B < %zu B", workspace_bytes, need);
-    MPSB_ARG(((uintptr_t)workspace & 15) == 0, "apply_gate2: workspace must be 16-byte aligned");
+    MPSB_ARG(((uintptr_t)workspace & 255) == 0, "apply_gate2: workspace must be 256-byte aligned");
     cf* ws = (cf*)workspace;
     cf* X = ws;                                              // [njobs][x_elems]
     cf* extra = ws + align_up(p.x_elems, 16) * (size_t)njobs;     // [njobs][extra]
-    int rc = launch_theta(descs_dev, ndesc, nbatch, d, chiL, chiM, chiR, left_canonical ? 0 : 1,
+    int rc;
+    if (tc)
+        rc = launch_theta_tc(descs_dev, ndesc, nbatch, chiL, chiM, chiR, left_canonical ? 0 : 1, X,
+                             (int64_t)align_up(p.x_elems, 16), (float*)((char*)workspace + need_svd), st);
+    else
+        rc = launch_theta(descs_dev, ndesc, nbatch, d, chiL, chiM, chiR, left_canonical ? 0 : 1,
                           X, (int64_t)align_up(p.x_elems, 16), st);
     if (rc) return rc;
     if (p.small) {
@@ -247,10 +263,35 @@ int mpsb_cgemm(const void* A, int64_t a_rs, int64_t a_cs, int conj_a, int64_t a_
 int mpsb_theta(const mpsb_gate2_desc* descs_dev, int ndesc, int nbatch, int d,
                int chiL, int chiM, int chiR, void* out, void* workspace, size_t workspace_bytes,
                void* stream) {
-    (void)workspace; (void)workspace_bytes;
     MPSB_ARG(descs_dev && out, "theta: NULL argument");
+    if (theta_uses_tc(d, chiL, chiM, chiR) && workspace != nullptr &&
+        workspace_bytes >= mpsb_theta_workspace_bytes(ndesc, nbatch, d, chiL, chiM, chiR)) {
+        MPSB_ARG(((uintptr_t)workspace & 255) == 0, "theta: workspace must be 256-byte aligned");
+        return launch_theta_tc(descs_dev, ndesc, nbatch, chiL, chiM, chiR, 0, (cf*)out, (int64_t)d * chiL * d * chiR,
+                               (float*)workspace, (cudaStream_t)stream);
+    }
     return launch_theta(descs_dev, ndesc, nbatch, d, chiL, chiM, chiR, 0, (cf*)out,
                         (int64_t)d * chiL * d * chiR, (cudaStream_t)stream);
+}
+
+size_t mpsb_theta_workspace_bytes(int ndesc, int nbatch, int d, int chiL, int chiM, int chiR) {
+    if (d != 2 || ndesc <= 0 || nbatch <= 0 || chiL <= 0 || chiM <= 0 || chiR <= 0) return 0;
+    return tc_theta_workspace_floats(ndesc * nbatch, chiL, chiM, chiR) * sizeof(float);
+}
+
+size_t mpsb_cgemm_tc_workspace_bytes(int M, int N, int K, int nbatch) {
+    if (M <= 0 || N <= 0 || K <= 0 || nbatch <= 0) return 0;
+    return tc_cgemm_workspace_floats(nbatch, M, N, K) * sizeof(float);
+}
+
+int mpsb_cgemm_tc(const void* A, int64_t a_bs, const void* B, int64_t b_bs, void* C, int64_t c_ld, int64_t c_bs,
+                  int M, int N, int K, int nbatch, void* workspace, size_t workspace_bytes, void* stream) {
+    MPSB_ARG(A && B && C, "cgemm_tc: NULL argument");
+    MPSB_ARG(workspace != nullptr && workspace_bytes >= mpsb_cgemm_tc_workspace_bytes(M, N, K, nbatch),
+             "cgemm_tc: workspace too small");
+    MPSB_ARG(((uintptr_t)workspace & 255) == 0, "cgemm_tc: workspace must be 256-byte aligned");
+    return launch_cgemm_tc((const cf*)A, a_bs, (const cf*)B, b_bs, (cf*)C, c_ld, c_bs, M, N, K, nbatch,
+                           (float*)workspace, (cudaStream_t)stream);
 }
 
 static size_t svd_x_elems(int m, int n) {

@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 PKG = os.path.dirname(HERE)
-SOURCES = ["api.cu", "cgemm.cu", "theta.cu", "svd_small.cu", "svd_large.cu", "site_ops.cu"]
+SOURCES = ["api.cu", "cgemm.cu", "theta.cu", "svd_small.cu", "svd_large.cu", "site_ops.cu", "tc_gemm.cu"]
 OUT = os.path.join(PKG, "libmpsim_b200.so")
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

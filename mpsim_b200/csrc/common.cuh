@@ -78,6 +78,12 @@ int launch_cgemm(const cf* A, int64_t a_rs, int64_t a_cs, int conj_a, int64_t a_
                  cudaStream_t st);
 int launch_theta(const mpsb_gate2_desc* descs, int ndesc, int nbatch, int d, int chiL, int chiM,
                  int chiR, int transpose_out, cf* out, int64_t out_job_stride, cudaStream_t st);
+size_t tc_theta_workspace_floats(int njobs, int chiL, int chiM, int chiR);
+size_t tc_cgemm_workspace_floats(int njobs, int M, int N, int K);
+int launch_theta_tc(const mpsb_gate2_desc* descs, int ndesc, int nbatch, int chiL, int chiM, int chiR,
+                    int transpose_out, cf* out, int64_t out_job_stride, float* work, cudaStream_t st);
+int launch_cgemm_tc(const cf* A, int64_t a_bs, const cf* B, int64_t b_bs, cf* C, int64_t c_ld, int64_t c_bs,
+                    int M, int N, int K, int nbatch, float* work, cudaStream_t st);
 size_t svd_small_global_z_elems(int nv, int L);
 int launch_svd_small(const cf* X, int64_t x_job_stride, int njobs, int nv, int L, int k,
                      int left_canonical, const mpsb_gate2_desc* descs, int ndesc, int nbatch,

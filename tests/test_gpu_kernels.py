@@ -57,6 +57,54 @@ def test_cgemm(M, N, K):
     np.testing.assert_allclose(dc.cpu().numpy(), ref, atol=2e-5 * np.sqrt(K) * 4)
 
 
+@pytest.mark.parametrize("M,N,K", [(128, 128, 16), (128, 128, 64), (256, 384, 100), (130, 70, 33), (512, 512, 256)])
+def test_cgemm_tc(M, N, K):
+    """tcgen05 3xTF32 complex GEMM (tc_gemm.cu) against numpy complex128: fp32-level accuracy."""
+    import torch
+    from mpsim_b200 import _lib
+    lib = _lib.load(require_device=True)
+    rng = np.random.RandomState(M + 3 * N + 7 * K)
+    nb = 3
+    a, b = _rand(rng, nb, M, K), _rand(rng, nb, K, N)
+    da, db = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda()
+    dc = torch.zeros((nb, M, N), dtype=torch.complex64, device="cuda")
+    ws = torch.empty(lib.mpsb_cgemm_tc_workspace_bytes(M, N, K, nb) + 256, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mpsb_cgemm_tc(da.data_ptr(), M * K, db.data_ptr(), K * N, dc.data_ptr(), N, M * N, M, N, K, nb,
+                                 ws.data_ptr(), ws.numel(), _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = a.astype(np.complex128) @ b.astype(np.complex128)
+    err = np.abs(dc.cpu().numpy() - ref).max()
+    assert err <= 2e-5 * np.sqrt(K), err          # a small multiple of the fp32 FFMA kernel's error (scripts/tc_accuracy.py)
+
+
+@pytest.mark.parametrize("chi", [(32, 16, 32), (64, 64, 64), (33, 17, 40), (128, 128, 128), (256, 200, 192)])
+def test_theta_tensor_core(chi):
+    """theta through the tcgen05 kernel (workspace given) against the einsum, incl. ragged shapes."""
+    import torch
+    from mpsim_b200 import _lib
+    lib = _lib.load(require_device=True)
+    cl, cm, cr = chi
+    d = 2
+    rng = np.random.RandomState(cl * 7 + cm * 3 + cr)
+    nb = 2
+    A, B = _rand(rng, nb, cl, d, cm), _rand(rng, nb, cm, d, cr)
+    G = _rand(rng, nb, d, d, d, d)
+    dA, dB, dG = (torch.from_numpy(x).cuda() for x in (A, B, G))
+    desc = np.zeros(1, dtype=_lib.GATE2_DESC)
+    desc[0] = (dA.data_ptr(), dB.data_ptr(), 0, 0, dG.data_ptr(), 0, cl * d * cm, cm * d * cr, 0, 0, d ** 4, 0)
+    ddesc = _lib.to_device_bytes(desc, "cuda")
+    out = torch.zeros((nb, d * cl, d * cr), dtype=torch.complex64, device="cuda")
+    nbytes = lib.mpsb_theta_workspace_bytes(1, nb, d, cl, cm, cr)
+    assert nbytes > 0
+    ws = torch.empty(nbytes + 256, dtype=torch.uint8, device="cuda")
+    _lib.check(lib.mpsb_theta(ddesc.data_ptr(), 1, nb, d, cl, cm, cr, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                              _lib.stream_ptr()))
+    torch.cuda.synchronize()
+    ref = np.einsum("bxypq,blpm,bmqr->blxyr", G.astype(np.complex128), A.astype(np.complex128), B.astype(np.complex128))
+    ref = ref.reshape(nb, cl * d, d * cr)
+    np.testing.assert_allclose(out.cpu().numpy(), ref, atol=3e-5 * np.sqrt(cm) * 4)
+
+
 @pytest.mark.parametrize("shape", [(2, 2), (4, 2), (2, 8), (8, 8), (16, 32), (32, 16), (64, 64), (128, 64),
                                    (64, 128), (100, 36), (128, 128)])
 @pytest.mark.parametrize("lc", [1, 0])
