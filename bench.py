@@ -290,8 +290,16 @@ def time_secondary(torch, args, batch):
         ms = ev(lambda: _lib.check(lib.mpsb_theta(ddesc.data_ptr(), 1, B, d, chi, chi, chi, theta.data_ptr(), None, 0,
                                                   _lib.stream_ptr())))
         fl = flops_theta(d, chi, chi, chi) * B
-        out["theta_kernel"] = {"ms_per_launch": ms, "jobs": B, "tflops": fl / (ms * 1e-3) / 1e12,
-                               "note": "split-real FFMA tiles (round 1); flops = 8 d^2 chi^3 + 8 d^4 chi^2 per application"}
+        out["theta_kernel_ffma"] = {"ms_per_launch": ms, "jobs": B, "tflops": fl / (ms * 1e-3) / 1e12,
+                                    "note": "split-real FFMA tiles (used for d != 2 or chi < 32); flops = 8 d^2 chi^3 + 8 d^4 chi^2 per application"}
+        wsb = lib.mpsb_theta_workspace_bytes(1, B, d, chi, chi, chi)
+        if wsb:
+            tws = torch.empty(wsb + 256, dtype=torch.uint8, device=chain.device)
+            ms = ev(lambda: _lib.check(lib.mpsb_theta(ddesc.data_ptr(), 1, B, d, chi, chi, chi, theta.data_ptr(),
+                                                      tws.data_ptr(), tws.numel(), _lib.stream_ptr())))
+            out["theta_kernel"] = {"ms_per_launch": ms, "jobs": B, "tflops": fl / (ms * 1e-3) / 1e12,
+                                   "note": "tcgen05 3xTF32 (operand split + TMA/TMEM GEMM + gate epilogue), the path mpsb_apply_gate2 uses"}
+            del tws
         # one-qudit gate on that site of every member: 16*d*chiL*chiR bytes per site
         g1 = torch.from_numpy(np.tile(np.array([1, 1, 1, -1], dtype=np.complex64) / np.sqrt(2), (B, 1))).to(chain.device)
         d1 = np.zeros(1, dtype=_lib.GATE1_DESC)
@@ -303,6 +311,70 @@ def time_secondary(torch, args, batch):
     ms = ev(lambda: chain.norms(), reps=3)
     site_bytes = sum(8.0 * chain.site_elems(i) for i in range(chain.n)) * B
     out["norm_chain"] = {"ms": ms, "launches": 2 * chain.n + 2, "gbs_sites_read_once": site_bytes / (ms * 1e-3) / 1e9}
+    return out
+
+
+def measure_tf32_peak(torch):
+    """Dense TF32 tensor-core throughput measured live (cuBLAS fp32 GEMM with TF32 allowed): the
+    'complex tensor-core peak' of SURVEY.md 8(d) is this / 3 (three TF32 products per fp32 product)."""
+    n = 8192
+    a = torch.randn((n, n), device="cuda", dtype=torch.float32)
+    b = torch.randn((n, n), device="cuda", dtype=torch.float32)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        torch.matmul(a, b)
+        torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        return best
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def time_theta_tc(torch, tf32_peak):
+    """theta contraction alone at the large shapes of BASELINE.json (chi = 256: configs[2], 50
+    disjoint bonds of one layer; chi = 1024: configs[4], 8 bonds), tensor-core kernel, CUDA events.
+    frac = achieved / (measured dense TF32 / 3)."""
+    from mpsim_b200 import _lib
+    lib = _lib.load(require_device=True)
+    out = {}
+    for chi, jobs in ((256, 50), (1024, 8)):
+        d = 2
+        A = torch.randn((jobs, chi, d, chi), dtype=torch.complex64, device="cuda")
+        Bm = torch.randn((jobs, chi, d, chi), dtype=torch.complex64, device="cuda")
+        G = torch.from_numpy(haar_gates(jobs, np.random.default_rng(11)).reshape(jobs, 16)).cuda()
+        desc = np.zeros(1, dtype=_lib.GATE2_DESC)
+        desc[0] = (A.data_ptr(), Bm.data_ptr(), 0, 0, G.data_ptr(), 0, chi * d * chi, chi * d * chi, 0, 0, 16, 0)
+        ddesc = _lib.to_device_bytes(desc, "cuda")
+        theta = torch.empty((jobs, d * chi, d * chi), dtype=torch.complex64, device="cuda")
+        ws = torch.empty(lib.mpsb_theta_workspace_bytes(1, jobs, d, chi, chi, chi) + 256, dtype=torch.uint8, device="cuda")
+
+        def run():
+            _lib.check(lib.mpsb_theta(ddesc.data_ptr(), 1, jobs, d, chi, chi, chi, theta.data_ptr(), ws.data_ptr(),
+                                      ws.numel(), _lib.stream_ptr()))
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            run()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        fl = flops_theta(d, chi, chi, chi) * jobs
+        tf = fl / (ms * 1e-3) / 1e12
+        out[f"chi{chi}"] = {"jobs": jobs, "ms_per_launch": ms, "tflops_complex_equivalent": tf,
+                            "complex_tensor_core_peak_tflops": tf32_peak / 3.0, "frac_of_complex_peak": tf / (tf32_peak / 3.0),
+                            "note": "includes the operand split / transpose kernels; operands %.0f MB > L2 at chi=1024"
+                                    % (2 * jobs * chi * d * chi * 8 / 1e6)}
+        del A, Bm, theta, ws
     return out
 
 
@@ -446,7 +518,12 @@ def run_our_arm(args):
     if rank == 0:
         launches_per_step = 0
         for L in cp.launches:
-            launches_per_step += 1 if L[0] == "g1" else 2
+            if L[0] == "g1":
+                launches_per_step += 1
+            else:
+                _, _, _, chiL, chiM, chiR, _, _ = L
+                tc = chiL >= 32 and chiR >= 32 and chiM >= 16        # api.cu: theta_uses_tc (d = 2)
+                launches_per_step += (3 if tc else 1) + 1            # theta (split A, split/transpose B, GEMM | FFMA) + SVD
         launches_per_step += 2 * n + 2                # norm chain: 2 GEMMs per site + init + gather
         # dominant kernel roofline (measured live, CUDA events on the launching stream)
         dom = time_dominant_kernel(torch, args, batch)
@@ -457,7 +534,10 @@ def run_our_arm(args):
             achieved = fl / (dom["ms_per_launch"] * 1e-3) / 1e12
             roof = {"kernel": "svd_small_kernel (single-CTA QR + one-sided Jacobi, 128x128 complex64)",
                     "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
-                    "frac": achieved / fp32_peak, "traffic": None,
+                    "frac": achieved / fp32_peak,
+                    # dram__bytes_read.sum + dram__bytes_write.sum of the 148-job capture in
+                    # profiles/r1_svd_small_ncu_full.txt (19.53 MB + 0), scaled to this launch's job count
+                    "traffic": 19.528e6 / 148.0 * dom["jobs_per_launch"],
                     "note": "achieved = LAPACK-equivalent flops 4(14 mx mn^2 + 8 mn^3) x jobs / CUDA-event launch "
                             "time; peak = fp32 SGEMM throughput measured live in this run (MEASURED_PEAKS.json "
                             "records only HBM and bf16); the kernel is FFMA/shuffle bound in shared memory, "
@@ -469,6 +549,9 @@ def run_our_arm(args):
             del batch
             torch.cuda.empty_cache()
             secondary["chi256"] = time_chi256(torch)
+            tf32_peak = measure_tf32_peak(torch)
+            secondary["theta_tensor_core"] = time_theta_tc(torch, tf32_peak)
+            secondary["tf32_tflops_measured_here"] = tf32_peak
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

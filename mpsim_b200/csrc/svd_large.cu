@@ -14,6 +14,7 @@
 // (mpsim/core.py:1132-1152).  Round 1: FFMA tiles; the Gram/apply steps are the candidates for
 // tcgen05 3xTF32.
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace {
 
@@ -437,11 +438,14 @@ int launch_svd_large(cf* X, int64_t x_job_stride, int njobs, int nv, int L, int 
     MPSB_LAUNCH_CHECK("bj_init_kernel");
     const int nrounds = lo.nb > 2 ? lo.nb - 1 : 1;
     const int ntx = (L + CT - 1) / CT, ntz = (lo.nvp + CT - 1) / CT;
-    for (int sweep = 0; sweep < MAX_OUTER; ++sweep) {
+    int skip = 0, max_outer = MAX_OUTER;         // timing experiments only
+    if (const char* e = getenv("MPSB_LARGE_SKIP")) skip = atoi(e);
+    if (const char* e = getenv("MPSB_LARGE_SWEEPS")) max_outer = atoi(e);
+    for (int sweep = 0; sweep < max_outer; ++sweep) {
         for (int r = 0; r < nrounds; ++r) {
-            bj_gram_kernel<<<dim3(lo.npairs, njobs), LT, 0, st>>>(p, r);
-            bj_evd_kernel<<<dim3(lo.npairs, njobs), LT, 0, st>>>(p);
-            bj_apply_kernel<<<dim3(ntx + ntz, lo.npairs, njobs), LT, 0, st>>>(p, r, ntx);
+            if (!(skip & 1)) bj_gram_kernel<<<dim3(lo.npairs, njobs), LT, 0, st>>>(p, r);
+            if (!(skip & 2)) bj_evd_kernel<<<dim3(lo.npairs, njobs), LT, 0, st>>>(p);
+            if (!(skip & 4)) bj_apply_kernel<<<dim3(ntx + ntz, lo.npairs, njobs), LT, 0, st>>>(p, r, ntx);
         }
         bj_sweep_end_kernel<<<(njobs + 127) / 128, 128, 0, st>>>(p, njobs);
     }

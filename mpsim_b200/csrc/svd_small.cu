@@ -41,7 +41,7 @@ constexpr int XS_ELEMS = 128 * (XCH + 1);   // >= XCH * (128 + 4)
 constexpr float BIG2 = 1e-4f * 1e-4f;       // a sweep without a rotation above this is the last
 
 // phase boundaries of CTA 0 (clock64), read back by mpsb_debug_phase_clocks: a profiling aid
-__device__ long long g_phase_clk[16];
+__device__ long long g_phase_clk[32];
 __device__ int g_dbg_flags;      // timing experiments only (set through mpsb_debug_set_flags)
 #define PHASE_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_clk[i] = clock64(); } while (0)
 
@@ -161,6 +161,10 @@ __device__ __forceinline__ int sub_round_y(cf (&y)[8][EPL], float (&a)[8], float
         }
     }
     return __popc(flags);
+}
+
+__device__ __forceinline__ void named_barrier_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 // threads per column for the Householder passes: the largest power of two <= 32 with ncols * tpc <= ST
@@ -301,6 +305,9 @@ __device__ __noinline__ void householder(cf* A, int LS, int nrows, int ncols, in
     for (int j = 0; j < nsteps; ++j) {
         const int cur = j & 1, nxt = cur ^ 1;
         const cf* vbl = vbuf + cur * VB;
+        // step-10 timeline of the threads that publish column 11 (profiling aid, CTA 0, MODE 0)
+        const bool probe = MODE == 0 && j == 10 && blockIdx.x == 0 && mine && col == 11 && sub == 0;
+        if (probe) g_phase_clk[16] = clock64();
         float tail2 = 0.f;
         if (!(dbg & 4)) {
 #pragma unroll
@@ -328,11 +335,15 @@ __device__ __noinline__ void householder(cf* A, int LS, int nrows, int ncols, in
         } else if (reflect) { v0 = x0; tau = 0.5f; }
         if (MODE == 1 && tid == 0) { tau_arr[j] = tau; v0_arr[j] = v0; }
         if (mine && col == j) { my_alpha = alpha; my_v0 = v0; my_reflect = reflect; }
+        if (probe) g_phase_clk[17] = clock64();
         if (mine && col > j) {
             if (reflect && !(dbg & 1)) reflect_column(vbl + sub, j, v0, tau);
+            if (probe) g_phase_clk[18] = clock64();
             if (col == j + 1 && j + 1 < nsteps && !(dbg & 2)) publish(j + 1, vbuf + nxt * VB + sub, scal + nxt * 4);
         }
+        if (probe) g_phase_clk[19] = clock64();
         __syncthreads();
+        if (probe) g_phase_clk[20] = clock64();
     }
     if (MODE == 1) {
         // backward: Q <- H_j Q for j = k-1 .. 0, in the same registers
@@ -445,8 +456,12 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
             }
             __syncthreads();
             bool big = false;
-            // (per-block round counters instead of the block-wide barrier were tried and were
-            //  3x slower: the polling warps take issue slots from the ones they wait for)
+            // Rounds are separated by PAIRWISE named barriers, not by a block-wide one: in the circle
+            // method group g takes its two blocks of the next round from groups g-1 and g+1 only, so
+            // a warp syncs with its two neighbours (edge (g, g+1) = barrier 1 + g, even warps right
+            // edge first, odd warps left edge first) and the warps drift apart by whole rounds; their
+            // shuffle / MUFU latencies then overlap instead of all of them stalling in the same phase.
+            // (Polling per-block round counters in shared memory was tried and was 3x slower.)
             for (int r = 0; r < nrounds; ++r) {
                 for (int g = warp; g < ngroups; g += NW) {
                     int I, Jb;
@@ -493,8 +508,17 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
                         for (int i = 1; i < 8; ++i) if (lane == i) am = a[i];
                         if (lane < 8) nrm[lane < 4 ? 4 * I + lane : 4 * Jb + lane - 4] = am;
                     }
+                    if (r + 1 < nrounds) {
+                        const bool has_r = g + 1 < ngroups, has_l = g > 0;
+                        if (g & 1) {
+                            if (has_l) named_barrier_sync(g, 64);
+                            if (has_r) named_barrier_sync(g + 1, 64);
+                        } else {
+                            if (has_r) named_barrier_sync(g + 1, 64);
+                            if (has_l) named_barrier_sync(g, 64);
+                        }
+                    }
                 }
-                __syncthreads();
             }
             sweeps = sweep + 1;
             if (!__syncthreads_or(big ? 1 : 0)) { status = 0; break; }
@@ -687,7 +711,7 @@ extern "C" int mpsb_debug_set_flags(int flags) {
 }
 
 extern "C" int mpsb_debug_phase_clocks(long long* out16) {
-    return (int)cudaMemcpyFromSymbol(out16, g_phase_clk, sizeof(long long) * 16);
+    return (int)cudaMemcpyFromSymbol(out16, g_phase_clk, sizeof(long long) * 32);
 }
 
 // (the Z spill of the first implementation is gone: nothing is needed in global memory)

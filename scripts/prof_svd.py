@@ -34,8 +34,9 @@ for _ in range(reps):
     print("ms", e0.elapsed_time(e1), "sweeps", info[:, 1].float().mean().item(), "status", int(info[:, 0].sum()))
 
 import ctypes
-clk = (ctypes.c_longlong * 16)()
+clk = (ctypes.c_longlong * 32)()
 if hasattr(lib, "mpsb_debug_phase_clocks") and lib.mpsb_debug_phase_clocks(clk) == 0:
     names = ["load", "qr1", "jacobi", "sort", "W=XV", "qr2+formQ", "P=QhX", "write"]
     c = list(clk)
+    print("householder step 10 (publisher thread): scalars %d reflect %d publish %d barrier %d" % (c[17] - c[16], c[18] - c[17], c[19] - c[18], c[20] - c[19]))
     print("phase cycles (CTA 0):", {n: c[i + 1] - c[i] for i, n in enumerate(names)}, "total", c[8] - c[0])
