@@ -14,6 +14,7 @@
 // (mpsim/core.py:1132-1152).  Round 1: FFMA tiles; the Gram/apply steps are the candidates for
 // tcgen05 3xTF32.
 #include "common.cuh"
+#include <vector>
 #include <stdlib.h>
 
 namespace {
@@ -118,40 +119,42 @@ __device__ __forceinline__ void evd_rot_params(float a, float b, float gr, float
 }
 
 // Two-sided Jacobi eigen-decomposition of the P x P Hermitian Gram matrix: Q G Q^H = diag.
-__global__ void __launch_bounds__(LT) bj_evd_kernel(LargeParams p) {
-    const int job = blockIdx.y, g = blockIdx.x;
+// ONE WARP per (job, pair) problem, G and Q in that warp's slice of shared memory, only
+// __syncwarp between the phases of a rotation set (the first version used a 256-thread CTA per
+// problem with three block-wide barriers per rotation set and took ~0.5 ms per problem: 80 % of a
+// round).  Per set of 16 disjoint pairs: lanes 0-15 compute the rotations, then lane = column
+// updates the rows of G and Q, then lane = row updates the columns of G.
+constexpr int EW = 4;                        // warps (problems) per CTA (69 KB of shared memory: 3 CTAs per SM)
+constexpr int EVD_SMEM_PER_WARP = 2 * P * (P + 1) * (int)sizeof(cf) + 16 * 16 + 16 * 4;
+
+__global__ void __launch_bounds__(EW * 32) bj_evd_kernel(LargeParams p, int nproblems) {
+    extern __shared__ float4 evd_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int prob = blockIdx.x * EW + warp;
+    if (prob >= nproblems) return;
+    const int job = prob / p.npairs, g = prob % p.npairs;
     if (!p.misc[job].active) return;
-    __shared__ cf Gs[P][P + 1];
-    __shared__ cf Qs[P][P + 1];
-    __shared__ float rc[P / 2], rsr[P / 2], rsi[P / 2];
-    __shared__ int rp[P / 2], rq[P / 2];
-    __shared__ float lam[P];
-    __shared__ int cnt[2];
-    __shared__ float red[LT / 32];
-    const int tid = threadIdx.x;
+    char* base = (char*)evd_smem + (size_t)warp * EVD_SMEM_PER_WARP;
+    float4* prm = (float4*)base;                              // [16] (c, s.re, s.im, rotate?)
+    int* pidx = (int*)(base + 16 * 16);                       // [16] p | q << 8
+    cf (*Gs)[P + 1] = (cf (*)[P + 1])(base + 16 * 16 + 16 * 4);
+    cf (*Qs)[P + 1] = Gs + P;
     cf* G = p.G + (size_t)job * p.g_stride + (size_t)g * P * P;
     cf* Qo = p.Q + (size_t)job * p.g_stride + (size_t)g * P * P;
-    // load, scaled by a power of two so that max|G| is in [1, 2)
+    // load (lane = column), scaled by a power of two so that max|G| is in [1, 2)
     float mx = 0.f;
-    for (int e = tid; e < P * P; e += LT) { cf v = G[e]; mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))); }
+    for (int i = 0; i < P; ++i) { cf v = G[i * P + lane]; mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))); }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if ((tid & 31) == 0) red[tid >> 5] = mx;
-    if (tid < 2) cnt[tid] = 0;
-    __syncthreads();
-    mx = 0.f;
-#pragma unroll
-    for (int w = 0; w < LT / 32; ++w) mx = fmaxf(mx, red[w]);
     int ex = 0;
     if (mx > 0.f && isfinite(mx)) (void)frexpf(mx, &ex);
     const float sc = mx > 0.f ? ldexpf(1.0f, 1 - ex) : 1.0f;
-    for (int e = tid; e < P * P; e += LT) {
-        int i = e / P, j = e - i * P;
-        cf v = G[e];
-        Gs[i][j] = cf_make(v.x * sc, v.y * sc);
-        Qs[i][j] = cf_make(i == j ? 1.f : 0.f, 0.f);
+    for (int i = 0; i < P; ++i) {
+        cf v = G[i * P + lane];
+        Gs[i][lane] = cf_make(v.x * sc, v.y * sc);
+        Qs[i][lane] = cf_make(i == lane ? 1.f : 0.f, 0.f);
     }
-    __syncthreads();
+    __syncwarp();
     // Rotation criterion: |G_pq| > tol sqrt(G_pp G_qq)  AND  |G_pq| > eta sigma_max max(s_p, s_q).
     // The second (absolute) part matters for graded spectra: every GEMM that mixes a large row
     // into a small one leaves ~eps*sigma_max of noise in it, so |G_pq| of a small pair carries
@@ -165,92 +168,97 @@ __global__ void __launch_bounds__(LT) bj_evd_kernel(LargeParams p) {
     const float eta2g = ABS_ETA * ABS_ETA * gmax_s;
     int total_rot = 0;
     for (int sweep = 0; sweep < 24; ++sweep) {
+        int rot = 0;
         for (int r = 0; r < P - 1; ++r) {
-            if (tid < P / 2) {
+            bool dorot = false;
+            if (lane < P / 2) {
                 int a_, b_;
                 const int m = P - 1;
-                if (tid == 0) { a_ = m; b_ = r; } else { a_ = (r + tid) % m; b_ = (r - tid + m) % m; }
+                if (lane == 0) { a_ = m; b_ = r; } else { a_ = (r + lane) % m; b_ = (r - lane + m) % m; }
                 const int pp = min(a_, b_), qq = max(a_, b_);
-                float a = Gs[pp][pp].x, b = Gs[qq][qq].x;
-                cf gg = Gs[pp][qq];
-                float g2 = cf_abs2(gg);
+                const float a = Gs[pp][pp].x, b = Gs[qq][qq].x;
+                const cf gg = Gs[pp][qq];
+                const float g2 = cf_abs2(gg);
                 float c = 1.f, sr = 0.f, si = 0.f;
-                if (g2 > p.tol2 * a * b && g2 > eta2g * fmaxf(a, b) && g2 > 1e-30f) {
-                    evd_rot_params(a, b, gg.x, gg.y, g2, c, sr, si);
-                    atomicAdd(&cnt[sweep & 1], 1);
-                }
-                rp[tid] = pp; rq[tid] = qq; rc[tid] = c; rsr[tid] = sr; rsi[tid] = si;
+                dorot = g2 > p.tol2 * a * b && g2 > eta2g * fmaxf(a, b) && g2 > 1e-30f;
+                if (dorot) evd_rot_params(a, b, gg.x, gg.y, g2, c, sr, si);
+                prm[lane] = make_float4(c, sr, si, dorot ? 1.f : 0.f);
+                pidx[lane] = pp | (qq << 8);
             }
-            __syncthreads();
-            // rows: [g_p; g_q] <- J [g_p; g_q], same for Q
-            for (int e = tid; e < (P / 2) * P * 2; e += LT) {
-                int which = e / ((P / 2) * P);
-                int rem = e - which * (P / 2) * P;
-                int i = rem / P, col = rem - i * P;
-                float c = rc[i], sr = rsr[i], si = rsi[i];
-                if (sr == 0.f && si == 0.f) continue;
-                cf (*Mx)[P + 1] = which ? Qs : Gs;
-                cf x = Mx[rp[i]][col], y = Mx[rq[i]][col];
+            const unsigned bal = __ballot_sync(0xffffffffu, dorot);
+            if (bal == 0u) continue;                         // warp-uniform: nothing to rotate in this set
+            rot += __popc(bal);
+            __syncwarp();
+            // rows: [g_p; g_q] <- J [g_p; g_q], same for Q      (lane = column)
+#pragma unroll 4
+            for (int i = 0; i < P / 2; ++i) {
+                if (!((bal >> i) & 1u)) continue;
+                const float4 pr = prm[i];
+                const int ip = pidx[i] & 0xff, iq = pidx[i] >> 8;
+                cf x = Gs[ip][lane], y = Gs[iq][lane];
                 cf nx, ny;
-                nx.x = fmaf(c, x.x, fmaf(sr, y.x, -(si * y.y)));
-                nx.y = fmaf(c, x.y, fmaf(sr, y.y, si * y.x));
-                ny.x = fmaf(c, y.x, -fmaf(sr, x.x, si * x.y));
-                ny.y = fmaf(c, y.y, fmaf(si, x.x, -(sr * x.y)));
-                Mx[rp[i]][col] = nx; Mx[rq[i]][col] = ny;
+                nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, -(pr.z * y.y)));
+                nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, pr.z * y.x));
+                ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, pr.z * x.y));
+                ny.y = fmaf(pr.x, y.y, fmaf(pr.z, x.x, -(pr.y * x.y)));
+                Gs[ip][lane] = nx; Gs[iq][lane] = ny;
+                x = Qs[ip][lane]; y = Qs[iq][lane];
+                nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, -(pr.z * y.y)));
+                nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, pr.z * y.x));
+                ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, pr.z * x.y));
+                ny.y = fmaf(pr.x, y.y, fmaf(pr.z, x.x, -(pr.y * x.y)));
+                Qs[ip][lane] = nx; Qs[iq][lane] = ny;
             }
-            __syncthreads();
-            // columns: [g_.p, g_.q] <- [g_.p, g_.q] J^H :  p' = c p + conj(s) q ; q' = -s p + c q
-            for (int e = tid; e < (P / 2) * P; e += LT) {
-                int i = e / P, row = e - i * P;
-                float c = rc[i], sr = rsr[i], si = rsi[i];
-                if (sr == 0.f && si == 0.f) continue;
-                cf x = Gs[row][rp[i]], y = Gs[row][rq[i]];
+            __syncwarp();
+            // columns: [g_.p, g_.q] <- [g_.p, g_.q] J^H :  p' = c p + conj(s) q ; q' = -s p + c q   (lane = row)
+#pragma unroll 4
+            for (int i = 0; i < P / 2; ++i) {
+                if (!((bal >> i) & 1u)) continue;
+                const float4 pr = prm[i];
+                const int ip = pidx[i] & 0xff, iq = pidx[i] >> 8;
+                const cf x = Gs[lane][ip], y = Gs[lane][iq];
                 cf nx, ny;
-                nx.x = fmaf(c, x.x, fmaf(sr, y.x, si * y.y));
-                nx.y = fmaf(c, x.y, fmaf(sr, y.y, -(si * y.x)));
-                ny.x = fmaf(c, y.x, -fmaf(sr, x.x, -(si * x.y)));
-                ny.y = fmaf(c, y.y, -fmaf(sr, x.y, si * x.x));
-                Gs[row][rp[i]] = nx; Gs[row][rq[i]] = ny;
+                nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, pr.z * y.y));
+                nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, -(pr.z * y.x)));
+                ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, -(pr.z * x.y)));
+                ny.y = fmaf(pr.x, y.y, -fmaf(pr.y, x.y, pr.z * x.x));
+                Gs[lane][ip] = nx; Gs[lane][iq] = ny;
             }
-            __syncthreads();
+            __syncwarp();
         }
-        int rot = cnt[sweep & 1];
-        if (tid == 0) cnt[(sweep + 1) & 1] = 0;
         total_rot += rot;
-        __syncthreads();
         if (rot == 0) break;
     }
     // Q is written UNSORTED: small-angle rotations started from the identity keep Q close to
     // the identity, which the cyclic block method needs to converge (sorting the rows by
     // eigenvalue is a permutation far from the identity and makes the outer iteration cycle).
-    if (tid < P) lam[tid] = Gs[tid][tid].x;
-    __syncthreads();
+    float lam = Gs[lane][lane].x;
+    __syncwarp();
     // One Newton-Schulz step Q <- (3 Q - (Q Q^H) Q) / 2: the product of ~10^3 fp32 rotations is
     // unitary only to ~2e-6, and that error would random-walk into every row norm (= singular
     // value) over the ~400 block rotations of a solve; after the step Q is unitary to ~1e-7.
-    for (int e = tid; e < P * P; e += LT) {
-        int i = e / P, j = e - i * P;
+    // R = Q Q^H into Gs (lane = column j of R), then Qo = 1.5 Q - 0.5 R Q (lane = column j).
+    for (int i = 0; i < P; ++i) {
         cf r = cf_make(0.f, 0.f);
 #pragma unroll 8
-        for (int k = 0; k < P; ++k) r = cf_fma_conja(Qs[j][k], Qs[i][k], r);     // Q_ik conj(Q_jk)
-        Gs[i][j] = r;
+        for (int k = 0; k < P; ++k) r = cf_fma_conja(Qs[lane][k], Qs[i][k], r);     // Q_ik conj(Q_jk), j = lane
+        __syncwarp();
+        Gs[i][lane] = r;
     }
-    __syncthreads();
-    for (int e = tid; e < P * P; e += LT) {
-        int i = e / P, j = e - i * P;
+    __syncwarp();
+    for (int i = 0; i < P; ++i) {
         cf t = cf_make(0.f, 0.f);
 #pragma unroll 8
-        for (int k = 0; k < P; ++k) t = cf_fma(Gs[i][k], Qs[k][j], t);
-        cf q = Qs[i][j];
-        Qo[e] = cf_make(1.5f * q.x - 0.5f * t.x, 1.5f * q.y - 0.5f * t.y);
+        for (int k = 0; k < P; ++k) t = cf_fma(Gs[i][k], Qs[k][lane], t);
+        const cf q = Qs[i][lane];
+        Qo[i * P + lane] = cf_make(1.5f * q.x - 0.5f * t.x, 1.5f * q.y - 0.5f * t.y);
     }
-    __syncthreads();
-    if (tid == 0) {
-        float m = 0.f;
-        for (int i = 0; i < P; ++i) m = fmaxf(m, lam[i]);
-        atomicMax(&p.misc[job].gmax_next, __float_as_uint(fmaxf(m, 0.f) / sc));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) lam = fmaxf(lam, __shfl_xor_sync(0xffffffffu, lam, o));
+    if (lane == 0) {
+        atomicMax(&p.misc[job].gmax_next, __float_as_uint(fmaxf(lam, 0.f) / sc));
+        if (total_rot > 0) atomicAdd(&p.misc[job].rot, 1);
     }
-    if (tid == 0 && total_rot > 0) atomicAdd(&p.misc[job].rot, 1);
 }
 
 // rows of the pair, columns [c0, c0+CT) of [X | Z]:  T <- Q T   (in place)
@@ -438,16 +446,49 @@ int launch_svd_large(cf* X, int64_t x_job_stride, int njobs, int nv, int L, int 
     MPSB_LAUNCH_CHECK("bj_init_kernel");
     const int nrounds = lo.nb > 2 ? lo.nb - 1 : 1;
     const int ntx = (L + CT - 1) / CT, ntz = (lo.nvp + CT - 1) / CT;
+    const int nprob = njobs * lo.npairs;
+    MPSB_CUDA(cudaFuncSetAttribute(bj_evd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EW * EVD_SMEM_PER_WARP));
     int skip = 0, max_outer = MAX_OUTER;         // timing experiments only
     if (const char* e = getenv("MPSB_LARGE_SKIP")) skip = atoi(e);
     if (const char* e = getenv("MPSB_LARGE_SWEEPS")) max_outer = atoi(e);
+    // The sweep loop stops as soon as every job has converged instead of launching the remaining
+    // sweeps as no-ops (2 800 empty launches per call at the typical 10 sweeps): every second sweep
+    // the per-job flags are copied to pinned host memory behind an event, and the event of the
+    // PREVIOUS check is inspected -- the stream always has two sweeps queued, the GPU never idles.
+    static Misc* pinned = nullptr;
+    static size_t pinned_jobs = 0;
+    static cudaEvent_t ev[2] = {nullptr, nullptr};
+    if (pinned_jobs < (size_t)njobs) {
+        if (pinned) cudaFreeHost(pinned);
+        pinned_jobs = (size_t)njobs > 1024 ? (size_t)njobs : 1024;
+        MPSB_CUDA(cudaHostAlloc((void**)&pinned, 2 * pinned_jobs * sizeof(Misc), cudaHostAllocDefault));
+    }
+    if (!ev[0]) {
+        MPSB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+        MPSB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+    }
+    int pending = -1, slot = 0;
     for (int sweep = 0; sweep < max_outer; ++sweep) {
         for (int r = 0; r < nrounds; ++r) {
             if (!(skip & 1)) bj_gram_kernel<<<dim3(lo.npairs, njobs), LT, 0, st>>>(p, r);
-            if (!(skip & 2)) bj_evd_kernel<<<dim3(lo.npairs, njobs), LT, 0, st>>>(p);
+            if (!(skip & 2)) bj_evd_kernel<<<(nprob + EW - 1) / EW, EW * 32, EW * EVD_SMEM_PER_WARP, st>>>(p, nprob);
             if (!(skip & 4)) bj_apply_kernel<<<dim3(ntx + ntz, lo.npairs, njobs), LT, 0, st>>>(p, r, ntx);
         }
         bj_sweep_end_kernel<<<(njobs + 127) / 128, 128, 0, st>>>(p, njobs);
+        if (sweep >= 3 && (sweep & 1) && sweep + 1 < max_outer) {
+            if (pending >= 0) {
+                MPSB_CUDA(cudaEventSynchronize(ev[pending]));
+                const Misc* m = pinned + (size_t)pending * pinned_jobs;
+                bool any = false;
+                for (int j = 0; j < njobs; ++j) any = any || m[j].active != 0;
+                if (!any) break;
+            }
+            MPSB_CUDA(cudaMemcpyAsync(pinned + (size_t)slot * pinned_jobs, p.misc, sizeof(Misc) * (size_t)njobs,
+                                      cudaMemcpyDeviceToHost, st));
+            MPSB_CUDA(cudaEventRecord(ev[slot], st));
+            pending = slot;
+            slot ^= 1;
+        }
     }
     MPSB_LAUNCH_CHECK("bj_round kernels");
     // Every block rotation is a 32-term fp32 GEMM, so after several hundred of them Z has drifted
