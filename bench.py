@@ -405,6 +405,42 @@ def time_chi256(torch):
             "svd_not_converged": int((info[:, 0] != 0).sum()), "svd_mean_sweeps": float(info[:, 1].mean())}
 
 
+def time_chi1024(torch, jobs=4):
+    """chi = 1024 (the shape of BASELINE.json configs[4]): `jobs` adjacent applications on disjoint
+    bonds with random Gaussian sites (flat spectrum), through mpsb_apply_gate2 (tensor-core theta
+    + block-Jacobi SVD of the 2048 x 2048 theta + split), CUDA events, one warm-up call."""
+    from mpsim_b200 import _lib
+    lib = _lib.load(require_device=True)
+    d, chi = 2, 1024
+    A = torch.randn((jobs, chi, d, chi), dtype=torch.complex64, device="cuda") / np.sqrt(2 * chi)
+    Bm = torch.randn((jobs, chi, d, chi), dtype=torch.complex64, device="cuda") / np.sqrt(2 * chi)
+    A0, B0 = A.clone(), Bm.clone()
+    G = torch.from_numpy(haar_gates(jobs, np.random.default_rng(13)).reshape(jobs, 16)).cuda()
+    sv = torch.zeros((jobs, d * chi), dtype=torch.float32, device="cuda")
+    desc = np.zeros(1, dtype=_lib.GATE2_DESC)
+    se = chi * d * chi
+    desc[0] = (A.data_ptr(), Bm.data_ptr(), A.data_ptr(), Bm.data_ptr(), G.data_ptr(), sv.data_ptr(), se, se, se, se, 16, d * chi)
+    ddesc = _lib.to_device_bytes(desc, "cuda")
+    info = torch.zeros((jobs, 2), dtype=torch.int32, device="cuda")
+    ws = torch.empty(lib.mpsb_gate2_workspace_bytes(1, jobs, d, chi, chi, chi, chi) + 256, dtype=torch.uint8, device="cuda")
+    ms = None
+    for rep in range(2):
+        A.copy_(A0); Bm.copy_(B0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(lib.mpsb_apply_gate2(ddesc.data_ptr(), 1, jobs, d, chi, chi, chi, chi, 1, ws.data_ptr(), ws.numel(),
+                                        info.data_ptr(), _lib.stream_ptr()), "mpsb_apply_gate2")
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+    inf = info.cpu().numpy()
+    fl = (flops_svd_lapack(d * chi, d * chi) + flops_theta(d, chi, chi, chi)) * jobs
+    return {"workload": f"{jobs} disjoint bonds at chi=1024 (2048 x 2048 theta, k=1024), random sites",
+            "applications": jobs, "ms": ms, "applications_per_sec": jobs / (ms * 1e-3),
+            "lapack_equivalent_tflops": fl / (ms * 1e-3) / 1e12,
+            "svd_not_converged": int((inf[:, 0] != 0).sum()), "svd_mean_sweeps": float(inf[:, 1].mean())}
+
+
 def measure_fp32_peak(torch):
     """FP32 FFMA peak of this GPU measured live with torch (dependent-free FMA chains are not
     expressible in torch; use a large fp32 GEMM through cuBLAS as the FFMA proxy)."""
@@ -552,6 +588,7 @@ def run_our_arm(args):
             tf32_peak = measure_tf32_peak(torch)
             secondary["theta_tensor_core"] = time_theta_tc(torch, tf32_peak)
             secondary["tf32_tflops_measured_here"] = tf32_peak
+            secondary["chi1024"] = time_chi1024(torch)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
