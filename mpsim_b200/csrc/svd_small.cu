@@ -53,7 +53,7 @@ struct SvdSmallParams {
     cf* left; int64_t left_stride; cf* right; int64_t right_stride;   // output mode B
     float* svals; int64_t svals_stride;
     int32_t* info;
-    int max_sweeps; float tol2; int do_qr;
+    int max_sweeps; float tol2; int do_qr; int use_ns;
 };
 
 // (c, s, t|g|) of [[c, s], [-conj(s), c]] diagonalising [[a, g], [conj(g), b]]; s first, then
@@ -385,6 +385,79 @@ __device__ __noinline__ void householder(cf* A, int LS, int nrows, int ncols, in
     __syncthreads();
 }
 
+// Orthonormalisation of W [nv][k] (k <= 64) by one Newton-Schulz step, Q = W (3/2 I - 1/2 W^H W):
+// two small GEMMs instead of the 2k barrier-separated Householder steps.  W = X V_k S^-1 is
+// orthonormal up to E = W^H W - I with |E_ij| ~ 3e-6 sigma_i/sigma_j; the step squares that
+// (||Q^H Q - I|| <= 3/4 ||E||^2) and keeps span(Q) = span(W).  Only taken when ||E||_F < 2e-3
+// (measured on the data, block-uniform); otherwise W is left untouched and the caller runs the
+// Householder path, which also handles zero / noise columns.  M: scratch of 64 x 64.
+__device__ bool newton_schulz_q(cf* W, int LS, int nv, int k, cf* M, float* red) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    {
+        const int j = tid >> 3, jb = (tid & 7) * 8;            // G[j][jb .. jb+7]
+        cf acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc[u] = cf_make(0.f, 0.f);
+        if (j < k && jb < k) {
+            for (int a = 0; a < nv; ++a) {
+                const cf* wr = W + (size_t)a * LS;
+                const cf wj = wr[j];
+                const float4* w4 = reinterpret_cast<const float4*>(wr + jb);      // rows are 16-byte aligned (LS even)
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const float4 v = w4[u];
+                    acc[2 * u] = cf_fma_conja(wj, cf_make(v.x, v.y), acc[2 * u]);
+                    acc[2 * u + 1] = cf_fma_conja(wj, cf_make(v.z, v.w), acc[2 * u + 1]);
+                }
+            }
+        }
+        float e2 = 0.f;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            const bool ok = j < k && jb + u < k;
+            cf e = acc[u];
+            if (j == jb + u) e.x -= 1.0f;
+            if (ok) e2 += cf_abs2(e);
+            // M = 3/2 I - 1/2 G  (zero outside the k x k block)
+            M[j * 64 + jb + u] = ok ? cf_make((j == jb + u ? 1.5f : 0.f) - 0.5f * acc[u].x, -0.5f * acc[u].y) : cf_make(0.f, 0.f);
+        }
+        e2 = warp_sum(e2);
+        if (lane == 0) red[warp] = e2;
+    }
+    __syncthreads();
+    float e2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) e2 += red[w];
+    if (!(e2 < 2e-3f * 2e-3f)) { __syncthreads(); return false; }       // also catches NaN
+    {
+        const int a = tid >> 2, jq = (tid & 3) * 16;           // Q[a][jq .. jq+15]
+        cf acc[16];
+#pragma unroll
+        for (int u = 0; u < 16; ++u) acc[u] = cf_make(0.f, 0.f);
+        if (a < nv && jq < k) {
+            const cf* wr = W + (size_t)a * LS;
+            for (int jp = 0; jp < k; ++jp) {
+                const cf w = wr[jp];
+                const float4* m4 = reinterpret_cast<const float4*>(M + jp * 64 + jq);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const float4 v = m4[u];
+                    acc[2 * u] = cf_fma(w, cf_make(v.x, v.y), acc[2 * u]);
+                    acc[2 * u + 1] = cf_fma(w, cf_make(v.z, v.w), acc[2 * u + 1]);
+                }
+            }
+        }
+        __syncthreads();                                       // every read of W is done
+        if (a < nv) {
+#pragma unroll
+            for (int u = 0; u < 16; ++u)
+                if (jq + u < k) W[(size_t)a * LS + jq + u] = acc[u];
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
 __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
     extern __shared__ float4 smem_raw[];
     const int job = blockIdx.x;
@@ -631,7 +704,11 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
         __syncthreads();
     }
     PHASE_MARK(5);
-    householder<1>(Ys, LS, nv, k, k, vbuf, scal, tau_arr, v0_arr);
+    {
+        bool done = false;
+        if (k <= 64 && P.use_ns) done = newton_schulz_q(Ys, LS, nv, k, Xs, scal);
+        if (!done) householder<1>(Ys, LS, nv, k, k, vbuf, scal, tau_arr, v0_arr);
+    }
     PHASE_MARK(6);
 
     // ---- step 5: P = Q^H X (k x L) and the outputs ---------------------------------------------
@@ -739,9 +816,11 @@ int launch_svd_small(const cf* X, int64_t x_job_stride, int njobs, int nv, int L
     P.max_sweeps = 30;
     P.tol2 = 3e-6f * 3e-6f;
     P.do_qr = 1;
+    P.use_ns = 1;
     // debugging knobs (not part of the ABI)
     if (const char* e = getenv("MPSB_SVD_MAX_SWEEPS")) P.max_sweeps = atoi(e);
     if (const char* e = getenv("MPSB_SVD_NO_QR")) P.do_qr = atoi(e) ? 0 : 1;
+    if (const char* e = getenv("MPSB_SVD_NO_NS")) P.use_ns = atoi(e) ? 0 : 1;
     MPSB_CUDA(cudaFuncSetAttribute(svd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lo.smem));
     svd_small_kernel<<<njobs, ST, lo.smem, st>>>(P);
     MPSB_LAUNCH_CHECK("svd_small_kernel");
