@@ -581,6 +581,7 @@ def run_our_arm(args):
                     "ms_per_launch": dom["ms_per_launch"], "jobs_per_launch": dom["jobs_per_launch"],
                     "mean_sweeps": dom["mean_sweeps"]}
         secondary = time_secondary(torch, args, batch)
+        roof_theta = None
         if not args.no_extra:
             del batch
             torch.cuda.empty_cache()
@@ -589,6 +590,13 @@ def run_our_arm(args):
             secondary["theta_tensor_core"] = time_theta_tc(torch, tf32_peak)
             secondary["tf32_tflops_measured_here"] = tf32_peak
             secondary["chi1024"] = time_chi1024(torch)
+            t = secondary["theta_tensor_core"]["chi1024"]
+            roof_theta = {"kernel": "tc_cgemm_kernel + operand split (theta, chi=1024, 8 bonds)", "bound": "tensor",
+                          "achieved": t["tflops_complex_equivalent"], "peak": t["complex_tensor_core_peak_tflops"],
+                          "unit": "TFLOP/s", "frac": t["frac_of_complex_peak"], "traffic": 1.682e9 + 0.449e9,
+                          "note": "achieved = (8 d^2 chi^3 + 8 d^4 chi^2) x bonds / CUDA-event time; peak = dense TF32 "
+                                  "measured live in this run / 3 (3xTF32); traffic = dram read + write of the GEMM kernel "
+                                  "in profiles/r1_tc_theta_chi1024_ncu_full.txt (tensor pipe 70 % active there)"}
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -616,6 +624,7 @@ def run_our_arm(args):
             "roofline": roof,
             "cpu_baseline": cpu,
             "secondary": secondary,
+            "roofline_theta": roof_theta,
             "applications_per_step": apps_per_step_total,
             "svd_not_converged": not_converged, "svd_mean_sweeps": mean_sweeps,
             "norm_mean": float(norms_all.float().mean().item()),

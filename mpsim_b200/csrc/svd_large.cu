@@ -127,7 +127,7 @@ __device__ __forceinline__ void evd_rot_params(float a, float b, float gr, float
 constexpr int EW = 4;                        // warps (problems) per CTA (69 KB of shared memory: 3 CTAs per SM)
 constexpr int EVD_SMEM_PER_WARP = 2 * P * (P + 1) * (int)sizeof(cf) + 16 * 16 + 16 * 4;
 
-__global__ void __launch_bounds__(EW * 32) bj_evd_kernel(LargeParams p, int nproblems) {
+__global__ void __launch_bounds__(EW * 32) bj_evd_kernel(LargeParams p, int nproblems, int first_round) {
     extern __shared__ float4 evd_smem[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int prob = blockIdx.x * EW + warp;
@@ -166,68 +166,76 @@ __global__ void __launch_bounds__(EW * 32) bj_evd_kernel(LargeParams p, int npro
     // graded ones (tests/_jacobi_model.py notes; a blocked QR preconditioner is the next step).
     const float gmax_s = p.misc[job].gmax * sc;
     const float eta2g = ABS_ETA * ABS_ETA * gmax_s;
+    // ONE pass over the pairs of the two 16-row blocks, each rotation computed from the current
+    // (two-sidedly updated) Gram entries: the 16 cross sets (i, 16 + (i+s) mod 16), preceded in the
+    // first round of an outer sweep by the 15 intra-block sets (circle method inside each block).
+    // This is the scalar cyclic Jacobi sweep of svd_small.cu carried out on the Gram matrix: the
+    // outer iteration needs the same ~9 sweeps, but a pair step costs 16 (31) rotation sets instead
+    // of the 5 x 31 of a fully converged inner eigen-decomposition.
     int total_rot = 0;
-    for (int sweep = 0; sweep < 24; ++sweep) {
-        int rot = 0;
-        for (int r = 0; r < P - 1; ++r) {
-            bool dorot = false;
-            if (lane < P / 2) {
+    const int nsets = (first_round ? (BLK - 1) : 0) + BLK;
+    for (int t = 0; t < nsets; ++t) {
+        bool dorot = false;
+        if (lane < P / 2) {
+            int pp, qq;
+            if (first_round && t < BLK - 1) {
+                const int blk = lane >> 3, i = lane & 7, m = BLK - 1;
                 int a_, b_;
-                const int m = P - 1;
-                if (lane == 0) { a_ = m; b_ = r; } else { a_ = (r + lane) % m; b_ = (r - lane + m) % m; }
-                const int pp = min(a_, b_), qq = max(a_, b_);
-                const float a = Gs[pp][pp].x, b = Gs[qq][qq].x;
-                const cf gg = Gs[pp][qq];
-                const float g2 = cf_abs2(gg);
-                float c = 1.f, sr = 0.f, si = 0.f;
-                dorot = g2 > p.tol2 * a * b && g2 > eta2g * fmaxf(a, b) && g2 > 1e-30f;
-                if (dorot) evd_rot_params(a, b, gg.x, gg.y, g2, c, sr, si);
-                prm[lane] = make_float4(c, sr, si, dorot ? 1.f : 0.f);
-                pidx[lane] = pp | (qq << 8);
+                if (i == 0) { a_ = m; b_ = t; } else { a_ = (t + i) % m; b_ = (t - i + m) % m; }
+                pp = blk * BLK + min(a_, b_); qq = blk * BLK + max(a_, b_);
+            } else {
+                const int sft = first_round ? t - (BLK - 1) : t;
+                pp = lane; qq = BLK + ((lane + sft) & (BLK - 1));
             }
-            const unsigned bal = __ballot_sync(0xffffffffu, dorot);
-            if (bal == 0u) continue;                         // warp-uniform: nothing to rotate in this set
-            rot += __popc(bal);
-            __syncwarp();
-            // rows: [g_p; g_q] <- J [g_p; g_q], same for Q      (lane = column)
-#pragma unroll 4
-            for (int i = 0; i < P / 2; ++i) {
-                if (!((bal >> i) & 1u)) continue;
-                const float4 pr = prm[i];
-                const int ip = pidx[i] & 0xff, iq = pidx[i] >> 8;
-                cf x = Gs[ip][lane], y = Gs[iq][lane];
-                cf nx, ny;
-                nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, -(pr.z * y.y)));
-                nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, pr.z * y.x));
-                ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, pr.z * x.y));
-                ny.y = fmaf(pr.x, y.y, fmaf(pr.z, x.x, -(pr.y * x.y)));
-                Gs[ip][lane] = nx; Gs[iq][lane] = ny;
-                x = Qs[ip][lane]; y = Qs[iq][lane];
-                nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, -(pr.z * y.y)));
-                nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, pr.z * y.x));
-                ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, pr.z * x.y));
-                ny.y = fmaf(pr.x, y.y, fmaf(pr.z, x.x, -(pr.y * x.y)));
-                Qs[ip][lane] = nx; Qs[iq][lane] = ny;
-            }
-            __syncwarp();
-            // columns: [g_.p, g_.q] <- [g_.p, g_.q] J^H :  p' = c p + conj(s) q ; q' = -s p + c q   (lane = row)
-#pragma unroll 4
-            for (int i = 0; i < P / 2; ++i) {
-                if (!((bal >> i) & 1u)) continue;
-                const float4 pr = prm[i];
-                const int ip = pidx[i] & 0xff, iq = pidx[i] >> 8;
-                const cf x = Gs[lane][ip], y = Gs[lane][iq];
-                cf nx, ny;
-                nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, pr.z * y.y));
-                nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, -(pr.z * y.x)));
-                ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, -(pr.z * x.y)));
-                ny.y = fmaf(pr.x, y.y, -fmaf(pr.y, x.y, pr.z * x.x));
-                Gs[lane][ip] = nx; Gs[lane][iq] = ny;
-            }
-            __syncwarp();
+            const float a = Gs[pp][pp].x, b = Gs[qq][qq].x;
+            const cf gg = Gs[pp][qq];
+            const float g2 = cf_abs2(gg);
+            float c = 1.f, sr = 0.f, si = 0.f;
+            dorot = g2 > p.tol2 * a * b && g2 > eta2g * fmaxf(a, b) && g2 > 1e-30f;
+            if (dorot) evd_rot_params(a, b, gg.x, gg.y, g2, c, sr, si);
+            prm[lane] = make_float4(c, sr, si, dorot ? 1.f : 0.f);
+            pidx[lane] = pp | (qq << 8);
         }
-        total_rot += rot;
-        if (rot == 0) break;
+        const unsigned bal = __ballot_sync(0xffffffffu, dorot);
+        if (bal == 0u) continue;                         // warp-uniform: nothing to rotate in this set
+        total_rot += __popc(bal);
+        __syncwarp();
+        // rows: [g_p; g_q] <- J [g_p; g_q], same for Q      (lane = column)
+#pragma unroll 4
+        for (int i = 0; i < P / 2; ++i) {
+            if (!((bal >> i) & 1u)) continue;
+            const float4 pr = prm[i];
+            const int ip = pidx[i] & 0xff, iq = pidx[i] >> 8;
+            cf x = Gs[ip][lane], y = Gs[iq][lane];
+            cf nx, ny;
+            nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, -(pr.z * y.y)));
+            nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, pr.z * y.x));
+            ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, pr.z * x.y));
+            ny.y = fmaf(pr.x, y.y, fmaf(pr.z, x.x, -(pr.y * x.y)));
+            Gs[ip][lane] = nx; Gs[iq][lane] = ny;
+            x = Qs[ip][lane]; y = Qs[iq][lane];
+            nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, -(pr.z * y.y)));
+            nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, pr.z * y.x));
+            ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, pr.z * x.y));
+            ny.y = fmaf(pr.x, y.y, fmaf(pr.z, x.x, -(pr.y * x.y)));
+            Qs[ip][lane] = nx; Qs[iq][lane] = ny;
+        }
+        __syncwarp();
+        // columns: [g_.p, g_.q] <- [g_.p, g_.q] J^H :  p' = c p + conj(s) q ; q' = -s p + c q   (lane = row)
+#pragma unroll 4
+        for (int i = 0; i < P / 2; ++i) {
+            if (!((bal >> i) & 1u)) continue;
+            const float4 pr = prm[i];
+            const int ip = pidx[i] & 0xff, iq = pidx[i] >> 8;
+            const cf x = Gs[lane][ip], y = Gs[lane][iq];
+            cf nx, ny;
+            nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, pr.z * y.y));
+            nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, -(pr.z * y.x)));
+            ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, -(pr.z * x.y)));
+            ny.y = fmaf(pr.x, y.y, -fmaf(pr.y, x.y, pr.z * x.x));
+            Gs[lane][ip] = nx; Gs[lane][iq] = ny;
+        }
+        __syncwarp();
     }
     // Q is written UNSORTED: small-angle rotations started from the identity keep Q close to
     // the identity, which the cyclic block method needs to converge (sorting the rows by
@@ -471,7 +479,7 @@ int launch_svd_large(cf* X, int64_t x_job_stride, int njobs, int nv, int L, int 
     for (int sweep = 0; sweep < max_outer; ++sweep) {
         for (int r = 0; r < nrounds; ++r) {
             if (!(skip & 1)) bj_gram_kernel<<<dim3(lo.npairs, njobs), LT, 0, st>>>(p, r);
-            if (!(skip & 2)) bj_evd_kernel<<<(nprob + EW - 1) / EW, EW * 32, EW * EVD_SMEM_PER_WARP, st>>>(p, nprob);
+            if (!(skip & 2)) bj_evd_kernel<<<(nprob + EW - 1) / EW, EW * 32, EW * EVD_SMEM_PER_WARP, st>>>(p, nprob, r == 0 ? 1 : 0);
             if (!(skip & 4)) bj_apply_kernel<<<dim3(ntx + ntz, lo.npairs, njobs), LT, 0, st>>>(p, r, ntx);
         }
         bj_sweep_end_kernel<<<(njobs + 127) / 128, 128, 0, st>>>(p, njobs);
