@@ -120,6 +120,12 @@ class MPS:
         self._last = None            # last CompiledPlan (svals / status for inspection)
         self._record_svals = False
 
+    @staticmethod
+    def from_wavefunction(wavefunction: Any, nqudits: int, qudit_dimension: int = 2, tensor_prefix: str = "q",
+                          device: Any = None) -> "MPS":             # core.py:245-328
+        from mpsim_b200 import observables
+        return observables.from_wavefunction(MPS, wavefunction, nqudits, qudit_dimension, tensor_prefix, device)
+
     # ------------------------------------------------------------------ properties
     @property
     def nqudits(self) -> int:
@@ -215,6 +221,18 @@ class MPS:
         if np.isclose(norm, 0.0, atol=1e-15):
             raise ValueError("Norm of MPS is numerically zero, cannot renormalize.")
         self._chain.scale([(to_norm / norm) ** (1 / self.nqudits)])
+
+    def reduced_density_matrix(self, node_indices: Union[int, Sequence[int]]) -> np.ndarray:   # core.py:596-652
+        from mpsim_b200 import observables
+        return observables.reduced_density_matrix(self, node_indices)
+
+    def sample(self, nsamples: int, as_hist: bool = False, as_string: bool = False) -> Any:      # core.py:684-721
+        from mpsim_b200 import observables
+        return observables.sample(self, nsamples, as_hist, as_string)
+
+    def expectation(self, observable: MPSOperation) -> float:        # core.py:723-751
+        from mpsim_b200 import observables
+        return observables.expectation(self, observable)
 
     # ------------------------------------------------------------------ gate application
     def _execute(self, ops: Sequence[Tuple[np.ndarray, Tuple[int, ...], Dict[str, Any]]]) -> None:

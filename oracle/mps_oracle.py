@@ -300,6 +300,103 @@ class OracleMPS:
             else:                                                        # core.py:1271-1276
                 raise ValueError("Only one-qudit and two-qudit gates are supported.")
 
+    # ------------------------------------------------------------------ SURVEY.md 8(f) rows 2-3
+    @staticmethod
+    def from_wavefunction(wavefunction: Any, nqudits: int, qudit_dimension: int = 2,
+                          dtype: Any = None) -> "OracleMPS":      # core.py:245-328
+        if not isinstance(wavefunction, (list, tuple, np.ndarray)):
+            raise TypeError("Invalid type for wavefunction.")
+        wavefunction = np.array(wavefunction)
+        if len(wavefunction.shape) != 1:
+            raise ValueError("Invalid shape for wavefunction. Should be a vector.")
+        if nqudits < 2:
+            raise ValueError("At least two qudits are required.")
+        if wavefunction.size != qudit_dimension ** nqudits:
+            raise ValueError("Mismatch between wavefunction, qudit_dimension, and nqudits.")
+        d = qudit_dimension
+        mps = OracleMPS(nqudits, d, dtype)
+        # core.py:301-321: tn.split_node across every cut, no truncation; split_node hands
+        # sqrt(S) to both sides (tensornetwork 0.2.1 network_operations.split_node)
+        rest = wavefunction.reshape(1, -1)
+        sites = []
+        for _ in range(nqudits - 1):
+            chi = rest.shape[0]
+            mat = rest.reshape(chi * d, -1)
+            u, s, vh = np.linalg.svd(mat, full_matrices=False)
+            sq = np.sqrt(s).astype(mat.dtype)
+            sites.append((u * sq[None, :]).reshape(chi, d, s.size))
+            rest = sq[:, None] * vh
+        sites.append(rest.reshape(rest.shape[0], d, 1))
+        mps.sites = [mps._cast(a) for a in sites]
+        return mps
+
+    def reduced_density_matrix(self, node_indices: Any) -> np.ndarray:      # core.py:596-652
+        try:
+            node_indices = iter(node_indices)
+        except TypeError:
+            node_indices = [node_indices]
+        node_indices = tuple(node_indices)
+        if len(set(node_indices)) < len(node_indices):
+            raise ValueError("Node indices contains duplicates.")
+        if min(node_indices) < 0 or max(node_indices) > self.nqudits - 1:
+            raise IndexError("One or more invalid node indices.")
+        # env axes: open ket / bra legs in site order (labels), then ket bond, bra bond
+        env = np.ones((1, 1), dtype=self.sites[0].dtype)
+        labels: List[Any] = []
+        for i, a in enumerate(self.sites):
+            t = np.tensordot(env, a, [[env.ndim - 2], [0]])               # [..., a', p, b]
+            if i in node_indices:
+                env = np.tensordot(t, np.conj(a), [[t.ndim - 3], [0]])    # [..., p, b, p', b']
+                nd = env.ndim
+                env = np.moveaxis(env, nd - 2, nd - 3)                    # [..., p, p', b, b']
+                labels += [("k", i), ("b", i)]
+            else:
+                env = np.tensordot(t, np.conj(a), [[t.ndim - 3, t.ndim - 2], [0, 1]])   # [..., b, b']
+        env = env.reshape(env.shape[:-2])
+        order = [labels.index(("k", i)) for i in node_indices] + [labels.index(("b", i)) for i in node_indices]
+        env = np.transpose(env, order)
+        n = len(node_indices)
+        return env.reshape(self.d ** n, self.d ** n)
+
+    def sample_once(self, as_string: bool = False) -> Any:                 # core.py:654-682
+        # (sic) the reference draws every site from ITS OWN marginal of the unconditioned state
+        # (core.py:665 uses ``self``, the conditioned ``copy`` is never read): the same draws here
+        string = []
+        states = list(range(self.d))
+        for i in range(self.nqudits):
+            qubit = self.reduced_density_matrix(i).diagonal().real
+            string.append(np.random.choice(states, size=1, p=qubit)[0])
+        if as_string:
+            return "".join(str(bit) for bit in string)
+        return string
+
+    def sample(self, nsamples: int, as_hist: bool = False, as_string: bool = False) -> Any:   # core.py:684-721
+        if not isinstance(nsamples, int):
+            raise ValueError(f"Arg nsamples should be an int but is a {type(nsamples)}.")
+        if nsamples <= 0:
+            raise ValueError(f"Arg nsamples should be positive but is {nsamples}.")
+        if as_hist:
+            as_string = True
+        raw = [self.sample_once(as_string) for _ in range(nsamples)]
+        if as_hist:
+            hist: Dict[Any, int] = {}
+            for bitstring in raw:
+                hist[bitstring] = hist.get(bitstring, 0) + 1
+            return hist
+        return raw
+
+    def expectation(self, tensor: np.ndarray, indices: Sequence[int]) -> float:   # core.py:723-751
+        k = len(indices)
+        mat = np.asarray(tensor).reshape(self.d ** k, self.d ** k)
+        if not np.allclose(mat, mat.conj().T):
+            raise ValueError("Observable is not Hermitian.")
+        cp = self.copy()
+        if k == 1:
+            cp.apply_one_qudit_gate(np.asarray(tensor), indices[0])
+        else:
+            cp.apply_two_qudit_gate(np.asarray(tensor), indices[0], indices[1])
+        return self.inner_product(cp).real
+
     def copy(self) -> "OracleMPS":                          # core.py:1382-1384, 1420-1423
         new = OracleMPS(self.nqudits, self.d, self.dtype, self.track_norms)
         new.sites = [a.copy() for a in self.sites]

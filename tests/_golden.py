@@ -8,7 +8,9 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    """Circuit fixtures (observables.npz has its own loader, tests/_observables.py)."""
+    return sorted(n for n in (os.path.splitext(os.path.basename(p))[0]
+                              for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz"))) if n != "observables")
 
 
 class Golden:
