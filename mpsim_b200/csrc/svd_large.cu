@@ -5,10 +5,9 @@
 // that the heavy steps are GEMM-shaped:
 //   rows are grouped in blocks of B = P/2; block pairs follow the circle-method tournament;
 //   for every pair of a round (all pairs of all jobs in ONE launch per step):
-//     bj_gram  : G = Xp Xp^H                       (P x L) . (L x P)
-//     bj_evd   : G = Q^H diag Q by a two-sided Hermitian Jacobi in shared memory (P <= 64),
-//                rows of Q sorted by eigenvalue (de Rijk ordering)
-//     bj_apply : Xp <- Q Xp,  Zp <- Q Zp            (P x P) . (P x (L + nv)), in place
+//     bj_gram_evd : G = Xp Xp^H  (P x L) . (L x P), then ONE cyclic pass of two-sided Hermitian
+//                   Jacobi rotations on G in shared memory -> Q (P x P, near the identity)
+//     bj_apply    : Xp <- Q Xp,  Zp <- Q Zp            (P x P) . (P x (L + nv)), in place
 //   a job stops rotating (its launches become no-ops) after a sweep in which no pair rotated.
 // Replaces tn.split_node_full_svd -> np.linalg.svd for 2chi in {256, 512, 2048}
 // (mpsim/core.py:1132-1152).  Round 1: FFMA tiles; the Gram/apply steps are the candidates for
@@ -22,9 +21,9 @@ namespace {
 constexpr int P = 32;            // rows per block pair
 constexpr int BLK = P / 2;       // rows per block
 constexpr int LT = 256;          // threads
-constexpr int CT = 64;           // columns per apply tile
+constexpr int CT = 128;          // columns per apply tile
 constexpr int MAX_OUTER = 40;
-constexpr float ABS_ETA = 1e-6f;     // see bj_evd_kernel
+constexpr float ABS_ETA = 3e-7f;     // see bj_gram_evd_kernel
 
 struct Misc {                    // per job, lives in the workspace
     int active, rot, sweeps;
@@ -36,11 +35,12 @@ struct Misc {                    // per job, lives in the workspace
 struct LargeParams {
     cf* X; int64_t x_stride;     // [nvp][L]
     cf* Z; int64_t z_stride;     // [nvp][nvp]
-    cf* G; cf* Q; int64_t g_stride;   // [npairs][P][P] per job
+    cf* Q; int64_t g_stride;     // [npairs][P][P] per job
+    int* rotflag;                // [njobs][npairs]: did this round's pass rotate anything in the pair?
     float* sigma; int* perm; int64_t s_stride;   // [nvp]
     Misc* misc;
     int nv, L, nvp, nb, npairs;
-    float tol2;
+    float tol2, eta2;
 };
 
 __device__ __forceinline__ void pair_blocks(int nb, int r, int g, int& I, int& J) {
@@ -71,40 +71,6 @@ __global__ void bj_init_kernel(LargeParams p) {
     }
 }
 
-// G[i][j] = sum_c Xp[i][c] conj(Xp[j][c])
-__global__ void __launch_bounds__(LT) bj_gram_kernel(LargeParams p, int round) {
-    const int job = blockIdx.y, g = blockIdx.x;
-    if (!p.misc[job].active) return;
-    __shared__ cf Xs[P][33];
-    int I, J;
-    pair_blocks(p.nb, round, g, I, J);
-    const cf* X = p.X + (size_t)job * p.x_stride;
-    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;      // 16 x 16, 2 x 2 outputs each
-    cf acc[2][2] = {{cf_make(0.f, 0.f), cf_make(0.f, 0.f)}, {cf_make(0.f, 0.f), cf_make(0.f, 0.f)}};
-    for (int c0 = 0; c0 < p.L; c0 += 32) {
-        for (int e = threadIdx.x; e < P * 32; e += LT) {
-            int r = e >> 5, c = e & 31;
-            Xs[r][c] = (c0 + c < p.L) ? X[(size_t)pair_row(I, J, r) * p.L + c0 + c] : cf_make(0.f, 0.f);
-        }
-        __syncthreads();
-#pragma unroll 8
-        for (int c = 0; c < 32; ++c) {
-            cf a0 = Xs[ty * 2][c], a1 = Xs[ty * 2 + 1][c];
-            cf b0 = Xs[tx * 2][c], b1 = Xs[tx * 2 + 1][c];
-            acc[0][0] = cf_fma_conja(b0, a0, acc[0][0]);     // a * conj(b)
-            acc[0][1] = cf_fma_conja(b1, a0, acc[0][1]);
-            acc[1][0] = cf_fma_conja(b0, a1, acc[1][0]);
-            acc[1][1] = cf_fma_conja(b1, a1, acc[1][1]);
-        }
-        __syncthreads();
-    }
-    cf* G = p.G + (size_t)job * p.g_stride + (size_t)g * P * P;
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-        for (int j = 0; j < 2; ++j) G[(ty * 2 + i) * P + tx * 2 + j] = acc[i][j];
-}
-
 __device__ __forceinline__ void evd_rot_params(float a, float b, float gr, float gi, float g2,
                                                float& c, float& sr, float& si) {
     float rg = rsqrtf(g2);
@@ -118,162 +84,230 @@ __device__ __forceinline__ void evd_rot_params(float a, float b, float gr, float
     c = (h < 0.0625f) ? fmaf(-h, poly, 1.0f) : sqrtf(fmaf(-sr, sr, fmaf(-si, si, 1.0f)));
 }
 
-// Two-sided Jacobi eigen-decomposition of the P x P Hermitian Gram matrix: Q G Q^H = diag.
-// ONE WARP per (job, pair) problem, G and Q in that warp's slice of shared memory, only
-// __syncwarp between the phases of a rotation set (the first version used a 256-thread CTA per
-// problem with three block-wide barriers per rotation set and took ~0.5 ms per problem: 80 % of a
-// round).  Per set of 16 disjoint pairs: lanes 0-15 compute the rotations, then lane = column
-// updates the rows of G and Q, then lane = row updates the columns of G.
-constexpr int EW = 4;                        // warps (problems) per CTA (69 KB of shared memory: 3 CTAs per SM)
-constexpr int EVD_SMEM_PER_WARP = 2 * P * (P + 1) * (int)sizeof(cf) + 16 * 16 + 16 * 4;
+// One launch per round for all (job, pair) problems, a CTA of 256 threads each:
+//   1. Gram  G = Xp Xp^H  (G[i][j] = sum_c Xp[i][c] conj(Xp[j][c])): column tiles of GK staged in
+//      shared memory; the CTA is four groups of 64 threads, each group covers the whole 32 x 32
+//      output in 4 x 4 register tiles (rows ty + 8 i, tx + 8 j: conflict-free LDS, 8 LDS per
+//      64 FFMA) over its quarter of every tile; the four partial sums are added in a fixed order;
+//   2. warp 0: ONE cyclic pass of two-sided Hermitian Jacobi rotations over the pairs of the two
+//      16-row blocks (see below), G and Q in shared memory, only __syncwarp between the phases;
+//   3. all warps: one Newton-Schulz step on Q, Q to global, "rotated" flag for bj_apply_kernel.
+// (First version: three kernels -- Gram with 2 x 2 tiles, a 256-thread EVD with block-wide
+// barriers, later a warp-per-problem EVD kernel -- and a G round trip through L2.)
+constexpr int GK = 64;                       // columns per Gram tile
 
-__global__ void __launch_bounds__(EW * 32) bj_evd_kernel(LargeParams p, int nproblems, int first_round) {
-    extern __shared__ float4 evd_smem[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int prob = blockIdx.x * EW + warp;
-    if (prob >= nproblems) return;
-    const int job = prob / p.npairs, g = prob % p.npairs;
+__global__ void __launch_bounds__(LT) bj_gram_evd_kernel(LargeParams p, int round, int first_round) {
+    const int job = blockIdx.y, g = blockIdx.x;
     if (!p.misc[job].active) return;
-    char* base = (char*)evd_smem + (size_t)warp * EVD_SMEM_PER_WARP;
-    float4* prm = (float4*)base;                              // [16] (c, s.re, s.im, rotate?)
-    int* pidx = (int*)(base + 16 * 16);                       // [16] p | q << 8
-    cf (*Gs)[P + 1] = (cf (*)[P + 1])(base + 16 * 16 + 16 * 4);
-    cf (*Qs)[P + 1] = Gs + P;
-    cf* G = p.G + (size_t)job * p.g_stride + (size_t)g * P * P;
-    cf* Qo = p.Q + (size_t)job * p.g_stride + (size_t)g * P * P;
-    // load (lane = column), scaled by a power of two so that max|G| is in [1, 2)
-    float mx = 0.f;
-    for (int i = 0; i < P; ++i) { cf v = G[i * P + lane]; mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))); }
+    __shared__ cf Xs[P][GK + 1];
+    __shared__ cf Gs[P][P + 1];
+    __shared__ cf Qs[P][P + 1];
+    __shared__ float4 prm[P / 2];            // (c, s.re, s.im, rotate?)
+    __shared__ int pidx[P / 2];              // p | q << 8
+    __shared__ int s_rot;
+    __shared__ float s_sc;
+    int I, J;
+    pair_blocks(p.nb, round, g, I, J);
+    const cf* X = p.X + (size_t)job * p.x_stride;
+    const int grp = threadIdx.x >> 6, t64 = threadIdx.x & 63;
+    const int tx = t64 & 7, ty = t64 >> 3;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    cf acc[4][4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    int ex = 0;
-    if (mx > 0.f && isfinite(mx)) (void)frexpf(mx, &ex);
-    const float sc = mx > 0.f ? ldexpf(1.0f, 1 - ex) : 1.0f;
-    for (int i = 0; i < P; ++i) {
-        cf v = G[i * P + lane];
-        Gs[i][lane] = cf_make(v.x * sc, v.y * sc);
-        Qs[i][lane] = cf_make(i == lane ? 1.f : 0.f, 0.f);
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = cf_make(0.f, 0.f);
+    for (int c0 = 0; c0 < p.L; c0 += GK) {
+        for (int e = threadIdx.x; e < P * GK; e += LT) {
+            const int r = e / GK, c = e % GK;
+            Xs[r][c] = (c0 + c < p.L) ? X[(size_t)pair_row(I, J, r) * p.L + c0 + c] : cf_make(0.f, 0.f);
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int cc = 0; cc < GK / 4; ++cc) {
+            const int c = grp * (GK / 4) + cc;
+            cf a[4], b[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) a[i] = Xs[ty + 8 * i][c];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = Xs[tx + 8 * j][c];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = cf_fma_conja(b[j], a[i], acc[i][j]);     // a * conj(b)
+        }
+        __syncthreads();
     }
-    __syncwarp();
-    // Rotation criterion: |G_pq| > tol sqrt(G_pp G_qq)  AND  |G_pq| > eta sigma_max max(s_p, s_q).
-    // The second (absolute) part matters for graded spectra: every GEMM that mixes a large row
-    // into a small one leaves ~eps*sigma_max of noise in it, so |G_pq| of a small pair carries
-    // noise ~eps*sigma_max*max(s_p, s_q) and the relative criterion alone is never met in fp32.
-    // A row far below sigma_max keeps a component of up to eta*sigma_max along each larger row,
-    // i.e. an absolute error of ~eta*sqrt(nv)*sigma_max ~ 8e-6 sigma_max in the smallest singular
-    // values at eta = 1e-6 (measured; parity bound: 1e-5 sigma_max).  Without preconditioning the cyclic block method
-    // converges only linearly (~2x per sweep) until then: ~10 sweeps for flat spectra, ~17 for
-    // graded ones (tests/_jacobi_model.py notes; a blocked QR preconditioner is the next step).
-    const float gmax_s = p.misc[job].gmax * sc;
-    const float eta2g = ABS_ETA * ABS_ETA * gmax_s;
-    // ONE pass over the pairs of the two 16-row blocks, each rotation computed from the current
-    // (two-sidedly updated) Gram entries: the 16 cross sets (i, 16 + (i+s) mod 16), preceded in the
-    // first round of an outer sweep by the 15 intra-block sets (circle method inside each block).
-    // This is the scalar cyclic Jacobi sweep of svd_small.cu carried out on the Gram matrix: the
-    // outer iteration needs the same ~9 sweeps, but a pair step costs 16 (31) rotation sets instead
-    // of the 5 x 31 of a fully converged inner eigen-decomposition.
-    int total_rot = 0;
-    const int nsets = (first_round ? (BLK - 1) : 0) + BLK;
-    for (int t = 0; t < nsets; ++t) {
-        bool dorot = false;
-        if (lane < P / 2) {
-            int pp, qq;
-            if (first_round && t < BLK - 1) {
-                const int blk = lane >> 3, i = lane & 7, m = BLK - 1;
-                int a_, b_;
-                if (i == 0) { a_ = m; b_ = t; } else { a_ = (t + i) % m; b_ = (t - i + m) % m; }
-                pp = blk * BLK + min(a_, b_); qq = blk * BLK + max(a_, b_);
-            } else {
-                const int sft = first_round ? t - (BLK - 1) : t;
-                pp = lane; qq = BLK + ((lane + sft) & (BLK - 1));
+    for (int q = 0; q < 4; ++q) {
+        if (grp == q) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    cf& d = Gs[ty + 8 * i][tx + 8 * j];
+                    d = q == 0 ? acc[i][j] : cf_add(d, acc[i][j]);
+                }
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {
+        // scale by a power of two so that max|G| is in [1, 2)   (lane = column)
+        float mx = 0.f;
+        for (int i = 0; i < P; ++i) { cf v = Gs[i][lane]; mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))); }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        int ex = 0;
+        if (mx > 0.f && isfinite(mx)) (void)frexpf(mx, &ex);
+        const float sc = mx > 0.f ? ldexpf(1.0f, 1 - ex) : 1.0f;
+        for (int i = 0; i < P; ++i) {
+            cf v = Gs[i][lane];
+            Gs[i][lane] = cf_make(v.x * sc, v.y * sc);
+            Qs[i][lane] = cf_make(i == lane ? 1.f : 0.f, 0.f);
+        }
+        __syncwarp();
+        // Rotation criterion: |G_pq| > tol sqrt(G_pp G_qq)  AND  |G_pq| > eta sigma_max max(s_p, s_q).
+        // The second (absolute) part matters for graded spectra: every GEMM that mixes a large row
+        // into a small one leaves ~eps*sigma_max of noise in it, so |G_pq| of a small pair carries
+        // noise ~eps*sigma_max*max(s_p, s_q) and the relative criterion alone is never met in fp32.
+        // A row far below sigma_max keeps a component of up to eta*sigma_max along each larger row,
+        // i.e. an absolute error of ~eta*sqrt(nv)*sigma_max ~ 8e-6 sigma_max in the smallest singular
+        // values at eta = 1e-6 (measured; parity bound: 1e-5 sigma_max).  Without preconditioning the
+        // cyclic block method converges only linearly (~2x per sweep) until then: ~10 sweeps for flat
+        // spectra, ~17 for graded ones (tests/_jacobi_model.py notes).
+        const float gmax_s = p.misc[job].gmax * sc;
+        const float eta2g = p.eta2 * gmax_s;
+        // ONE pass over the pairs of the two 16-row blocks, each rotation computed from the current
+        // (two-sidedly updated) Gram entries: the 16 cross sets (i, 16 + (i+s) mod 16), preceded in the
+        // first round of an outer sweep by the 15 intra-block sets (circle method inside each block).
+        // This is the scalar cyclic Jacobi sweep of svd_small.cu carried out on the Gram matrix: the
+        // outer iteration needs the same ~9 sweeps, but a pair step costs 16 (31) rotation sets instead
+        // of the 5 x 31 of a fully converged inner eigen-decomposition.
+        int total_rot = 0;
+        const int nsets = (first_round ? (BLK - 1) : 0) + BLK;
+        for (int t = 0; t < nsets; ++t) {
+            bool dorot = false;
+            if (lane < P / 2) {
+                int pp, qq;
+                if (first_round && t < BLK - 1) {
+                    const int blk = lane >> 3, i = lane & 7, m = BLK - 1;
+                    int a_, b_;
+                    if (i == 0) { a_ = m; b_ = t; } else { a_ = (t + i) % m; b_ = (t - i + m) % m; }
+                    pp = blk * BLK + min(a_, b_); qq = blk * BLK + max(a_, b_);
+                } else {
+                    const int sft = first_round ? t - (BLK - 1) : t;
+                    pp = lane; qq = BLK + ((lane + sft) & (BLK - 1));
+                }
+                const float a = Gs[pp][pp].x, b = Gs[qq][qq].x;
+                const cf gg = Gs[pp][qq];
+                const float g2 = cf_abs2(gg);
+                float c = 1.f, sr = 0.f, si = 0.f;
+                dorot = g2 > p.tol2 * a * b && g2 > eta2g * fmaxf(a, b) && g2 > 1e-30f;
+                if (dorot) evd_rot_params(a, b, gg.x, gg.y, g2, c, sr, si);
+                prm[lane] = make_float4(c, sr, si, dorot ? 1.f : 0.f);
+                pidx[lane] = pp | (qq << 8);
             }
-            const float a = Gs[pp][pp].x, b = Gs[qq][qq].x;
-            const cf gg = Gs[pp][qq];
-            const float g2 = cf_abs2(gg);
-            float c = 1.f, sr = 0.f, si = 0.f;
-            dorot = g2 > p.tol2 * a * b && g2 > eta2g * fmaxf(a, b) && g2 > 1e-30f;
-            if (dorot) evd_rot_params(a, b, gg.x, gg.y, g2, c, sr, si);
-            prm[lane] = make_float4(c, sr, si, dorot ? 1.f : 0.f);
-            pidx[lane] = pp | (qq << 8);
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, dorot);
-        if (bal == 0u) continue;                         // warp-uniform: nothing to rotate in this set
-        total_rot += __popc(bal);
-        __syncwarp();
-        // rows: [g_p; g_q] <- J [g_p; g_q], same for Q      (lane = column)
+            const unsigned bal = __ballot_sync(0xffffffffu, dorot);
+            if (bal == 0u) continue;                         // warp-uniform: nothing to rotate in this set
+            total_rot += __popc(bal);
+            __syncwarp();
+            // rows: [g_p; g_q] <- J [g_p; g_q], same for Q      (lane = column)
 #pragma unroll 4
-        for (int i = 0; i < P / 2; ++i) {
-            if (!((bal >> i) & 1u)) continue;
-            const float4 pr = prm[i];
-            const int ip = pidx[i] & 0xff, iq = pidx[i] >> 8;
-            cf x = Gs[ip][lane], y = Gs[iq][lane];
-            cf nx, ny;
-            nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, -(pr.z * y.y)));
-            nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, pr.z * y.x));
-            ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, pr.z * x.y));
-            ny.y = fmaf(pr.x, y.y, fmaf(pr.z, x.x, -(pr.y * x.y)));
-            Gs[ip][lane] = nx; Gs[iq][lane] = ny;
-            x = Qs[ip][lane]; y = Qs[iq][lane];
-            nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, -(pr.z * y.y)));
-            nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, pr.z * y.x));
-            ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, pr.z * x.y));
-            ny.y = fmaf(pr.x, y.y, fmaf(pr.z, x.x, -(pr.y * x.y)));
-            Qs[ip][lane] = nx; Qs[iq][lane] = ny;
-        }
-        __syncwarp();
-        // columns: [g_.p, g_.q] <- [g_.p, g_.q] J^H :  p' = c p + conj(s) q ; q' = -s p + c q   (lane = row)
+            for (int i = 0; i < P / 2; ++i) {
+                if (!((bal >> i) & 1u)) continue;
+                const float4 pr = prm[i];
+                const int ip = pidx[i] & 0xff, iq = pidx[i] >> 8;
+                cf x = Gs[ip][lane], y = Gs[iq][lane];
+                cf nx, ny;
+                nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, -(pr.z * y.y)));
+                nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, pr.z * y.x));
+                ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, pr.z * x.y));
+                ny.y = fmaf(pr.x, y.y, fmaf(pr.z, x.x, -(pr.y * x.y)));
+                Gs[ip][lane] = nx; Gs[iq][lane] = ny;
+                x = Qs[ip][lane]; y = Qs[iq][lane];
+                nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, -(pr.z * y.y)));
+                nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, pr.z * y.x));
+                ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, pr.z * x.y));
+                ny.y = fmaf(pr.x, y.y, fmaf(pr.z, x.x, -(pr.y * x.y)));
+                Qs[ip][lane] = nx; Qs[iq][lane] = ny;
+            }
+            __syncwarp();
+            // columns: [g_.p, g_.q] <- [g_.p, g_.q] J^H :  p' = c p + conj(s) q ; q' = -s p + c q   (lane = row)
 #pragma unroll 4
-        for (int i = 0; i < P / 2; ++i) {
-            if (!((bal >> i) & 1u)) continue;
-            const float4 pr = prm[i];
-            const int ip = pidx[i] & 0xff, iq = pidx[i] >> 8;
-            const cf x = Gs[lane][ip], y = Gs[lane][iq];
-            cf nx, ny;
-            nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, pr.z * y.y));
-            nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, -(pr.z * y.x)));
-            ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, -(pr.z * x.y)));
-            ny.y = fmaf(pr.x, y.y, -fmaf(pr.y, x.y, pr.z * x.x));
-            Gs[lane][ip] = nx; Gs[lane][iq] = ny;
+            for (int i = 0; i < P / 2; ++i) {
+                if (!((bal >> i) & 1u)) continue;
+                const float4 pr = prm[i];
+                const int ip = pidx[i] & 0xff, iq = pidx[i] >> 8;
+                const cf x = Gs[lane][ip], y = Gs[lane][iq];
+                cf nx, ny;
+                nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, pr.z * y.y));
+                nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, -(pr.z * y.x)));
+                ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, -(pr.z * x.y)));
+                ny.y = fmaf(pr.x, y.y, -fmaf(pr.y, x.y, pr.z * x.x));
+                Gs[lane][ip] = nx; Gs[lane][iq] = ny;
+            }
+            __syncwarp();
         }
-        __syncwarp();
+        float lam = Gs[lane][lane].x;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) lam = fmaxf(lam, __shfl_xor_sync(0xffffffffu, lam, o));
+        if (lane == 0) {
+            atomicMax(&p.misc[job].gmax_next, __float_as_uint(fmaxf(lam, 0.f) / sc));
+            if (total_rot > 0) atomicAdd(&p.misc[job].rot, 1);
+            p.rotflag[(size_t)job * p.npairs + g] = total_rot > 0 ? 1 : 0;
+            s_rot = total_rot;
+        }
     }
+    __syncthreads();
+    if (s_rot == 0) return;                  // Q = I: bj_apply_kernel skips this pair
     // Q is written UNSORTED: small-angle rotations started from the identity keep Q close to
     // the identity, which the cyclic block method needs to converge (sorting the rows by
     // eigenvalue is a permutation far from the identity and makes the outer iteration cycle).
-    float lam = Gs[lane][lane].x;
-    __syncwarp();
     // One Newton-Schulz step Q <- (3 Q - (Q Q^H) Q) / 2: the product of ~10^3 fp32 rotations is
     // unitary only to ~2e-6, and that error would random-walk into every row norm (= singular
     // value) over the ~400 block rotations of a solve; after the step Q is unitary to ~1e-7.
-    // R = Q Q^H into Gs (lane = column j of R), then Qo = 1.5 Q - 0.5 R Q (lane = column j).
-    for (int i = 0; i < P; ++i) {
-        cf r = cf_make(0.f, 0.f);
-#pragma unroll 8
-        for (int k = 0; k < P; ++k) r = cf_fma_conja(Qs[lane][k], Qs[i][k], r);     // Q_ik conj(Q_jk), j = lane
-        __syncwarp();
-        Gs[i][lane] = r;
-    }
-    __syncwarp();
-    for (int i = 0; i < P; ++i) {
-        cf t = cf_make(0.f, 0.f);
-#pragma unroll 8
-        for (int k = 0; k < P; ++k) t = cf_fma(Gs[i][k], Qs[k][lane], t);
-        const cf q = Qs[i][lane];
-        Qo[i * P + lane] = cf_make(1.5f * q.x - 0.5f * t.x, 1.5f * q.y - 0.5f * t.y);
-    }
+    // R = Q Q^H into Gs, then Qo = 1.5 Q - 0.5 R Q   (thread = column `lane` of rows warp + 8 ii).
+    {
+        cf r[4];
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) lam = fmaxf(lam, __shfl_xor_sync(0xffffffffu, lam, o));
-    if (lane == 0) {
-        atomicMax(&p.misc[job].gmax_next, __float_as_uint(fmaxf(lam, 0.f) / sc));
-        if (total_rot > 0) atomicAdd(&p.misc[job].rot, 1);
+        for (int ii = 0; ii < 4; ++ii) r[ii] = cf_make(0.f, 0.f);
+#pragma unroll 8
+        for (int k = 0; k < P; ++k) {
+            const cf qj = Qs[lane][k];
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) r[ii] = cf_fma_conja(qj, Qs[warp + 8 * ii][k], r[ii]);   // Q_ik conj(Q_jk)
+        }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) Gs[warp + 8 * ii][lane] = r[ii];
+    }
+    __syncthreads();
+    {
+        cf* Qo = p.Q + (size_t)job * p.g_stride + (size_t)g * P * P;
+        cf t[4];
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) t[ii] = cf_make(0.f, 0.f);
+#pragma unroll 8
+        for (int k = 0; k < P; ++k) {
+            const cf qk = Qs[k][lane];
+#pragma unroll
+            for (int ii = 0; ii < 4; ++ii) t[ii] = cf_fma(Gs[warp + 8 * ii][k], qk, t[ii]);
+        }
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+            const int i = warp + 8 * ii;
+            const cf q = Qs[i][lane];
+            Qo[i * P + lane] = cf_make(1.5f * q.x - 0.5f * t[ii].x, 1.5f * q.y - 0.5f * t[ii].y);
+        }
     }
 }
 
-// rows of the pair, columns [c0, c0+CT) of [X | Z]:  T <- Q T   (in place)
+// rows of the pair, columns [c0, c0+CT) of [X | Z]:  T <- Q T   (in place).  A thread owns two
+// columns (c, c + CT/2) and 8 of the 32 output rows: per k two LDS.64 of T and four broadcast
+// LDS.128 of Q^T for 64 FFMA (the first version had one column per thread: 9 LDS per 32 FFMA).
 __global__ void __launch_bounds__(LT) bj_apply_kernel(LargeParams p, int round, int ntx) {
     const int job = blockIdx.z, g = blockIdx.y, tile = blockIdx.x;
     if (!p.misc[job].active) return;
-    __shared__ cf Qs[P][P + 1];
+    if (!p.rotflag[(size_t)job * p.npairs + g]) return;      // no rotation in this pair: Q = I
+    __shared__ __align__(16) cf Qt[P][P + 2];                // Qt[k][i] = Q[i][k]  (+2: 4-way instead of 32-way store conflicts)
     __shared__ cf Ts[P][CT + 1];
     int I, J;
     pair_blocks(p.nb, round, g, I, J);
@@ -281,26 +315,37 @@ __global__ void __launch_bounds__(LT) bj_apply_kernel(LargeParams p, int round, 
     if (tile < ntx) { base = p.X + (size_t)job * p.x_stride; ld = p.L; c0 = tile * CT; ncol = p.L; }
     else { base = p.Z + (size_t)job * p.z_stride; ld = p.nvp; c0 = (tile - ntx) * CT; ncol = p.nvp; }
     const cf* Q = p.Q + (size_t)job * p.g_stride + (size_t)g * P * P;
-    for (int e = threadIdx.x; e < P * P; e += LT) Qs[e / P][e % P] = Q[e];
+    for (int e = threadIdx.x; e < P * P; e += LT) Qt[e % P][e / P] = Q[e];
     for (int e = threadIdx.x; e < P * CT; e += LT) {
         int r = e / CT, c = e - r * CT;
         Ts[r][c] = (c0 + c < ncol) ? base[(size_t)pair_row(I, J, r) * ld + c0 + c] : cf_make(0.f, 0.f);
     }
     __syncthreads();
-    const int c = threadIdx.x % CT, rg = threadIdx.x / CT;        // 4 row groups of P/4 rows
-    constexpr int RPT = P / (LT / CT);
-    cf acc[RPT];
+    constexpr int HC = CT / 2;                               // 64 column pairs x 4 row groups
+    const int c = threadIdx.x % HC, rg = threadIdx.x / HC;
+    constexpr int RPT = P / (LT / HC);                       // 8 rows per thread
+    cf acc0[RPT], acc1[RPT];
 #pragma unroll
-    for (int i = 0; i < RPT; ++i) acc[i] = cf_make(0.f, 0.f);
+    for (int i = 0; i < RPT; ++i) { acc0[i] = cf_make(0.f, 0.f); acc1[i] = cf_make(0.f, 0.f); }
 #pragma unroll 4
     for (int k = 0; k < P; ++k) {
-        cf t = Ts[k][c];
+        const cf t0 = Ts[k][c], t1 = Ts[k][c + HC];
+        const float4* qrow = reinterpret_cast<const float4*>(&Qt[k][rg * RPT]);
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) acc[i] = cf_fma(Qs[rg * RPT + i][k], t, acc[i]);
+        for (int i2 = 0; i2 < RPT / 2; ++i2) {
+            const float4 q2 = qrow[i2];
+            const cf qa = cf_make(q2.x, q2.y), qb = cf_make(q2.z, q2.w);
+            acc0[2 * i2] = cf_fma(qa, t0, acc0[2 * i2]);
+            acc1[2 * i2] = cf_fma(qa, t1, acc1[2 * i2]);
+            acc0[2 * i2 + 1] = cf_fma(qb, t0, acc0[2 * i2 + 1]);
+            acc1[2 * i2 + 1] = cf_fma(qb, t1, acc1[2 * i2 + 1]);
+        }
     }
-    if (c0 + c < ncol) {
 #pragma unroll
-        for (int i = 0; i < RPT; ++i) base[(size_t)pair_row(I, J, rg * RPT + i) * ld + c0 + c] = acc[i];
+    for (int i = 0; i < RPT; ++i) {
+        cf* row = base + (size_t)pair_row(I, J, rg * RPT + i) * ld + c0;
+        if (c0 + c < ncol) row[c] = acc0[i];
+        if (c0 + c + HC < ncol) row[c + HC] = acc1[i];
     }
 }
 
@@ -432,7 +477,7 @@ int launch_svd_large(cf* X, int64_t x_job_stride, int njobs, int nv, int L, int 
     // workspace: [njobs][Z] [njobs][G] [njobs][Q] [njobs][sigma|perm] [njobs][misc]
     cf* w = work;
     p.Z = w; p.z_stride = (int64_t)lo.z; w += lo.z * njobs;
-    p.G = w; w += lo.g * njobs;
+    p.rotflag = (int*)w; w += lo.g * njobs;          // (region of the former G buffer)
     p.Q = w; w += lo.g * njobs;
     p.g_stride = (int64_t)lo.g;
     p.sigma = (float*)w; p.perm = (int*)((float*)w + (size_t)lo.s * njobs); p.s_stride = (int64_t)lo.s; w += lo.s * njobs;
@@ -446,6 +491,9 @@ int launch_svd_large(cf* X, int64_t x_job_stride, int njobs, int nv, int L, int 
     float floor_ = 4.0f * 5.96e-8f * sqrtf((float)L);
     if (floor_ > tol) tol = floor_;
     p.tol2 = tol * tol;
+    float eta = ABS_ETA;
+    if (const char* e = getenv("MPSB_LARGE_ETA")) eta = (float)atof(e);          // experiments only
+    p.eta2 = eta * eta;
 
     // keep the input: the weighted factor is recomputed from it at the end (see below)
     MPSB_CUDA(cudaMemcpy2DAsync(M0, lo.m0 * sizeof(cf), X, (size_t)x_job_stride * sizeof(cf),
@@ -454,8 +502,6 @@ int launch_svd_large(cf* X, int64_t x_job_stride, int njobs, int nv, int L, int 
     MPSB_LAUNCH_CHECK("bj_init_kernel");
     const int nrounds = lo.nb > 2 ? lo.nb - 1 : 1;
     const int ntx = (L + CT - 1) / CT, ntz = (lo.nvp + CT - 1) / CT;
-    const int nprob = njobs * lo.npairs;
-    MPSB_CUDA(cudaFuncSetAttribute(bj_evd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, EW * EVD_SMEM_PER_WARP));
     int skip = 0, max_outer = MAX_OUTER;         // timing experiments only
     if (const char* e = getenv("MPSB_LARGE_SKIP")) skip = atoi(e);
     if (const char* e = getenv("MPSB_LARGE_SWEEPS")) max_outer = atoi(e);
@@ -478,8 +524,7 @@ int launch_svd_large(cf* X, int64_t x_job_stride, int njobs, int nv, int L, int 
     int pending = -1, slot = 0;
     for (int sweep = 0; sweep < max_outer; ++sweep) {
         for (int r = 0; r < nrounds; ++r) {
-            if (!(skip & 1)) bj_gram_kernel<<<dim3(lo.npairs, njobs), LT, 0, st>>>(p, r);
-            if (!(skip & 2)) bj_evd_kernel<<<(nprob + EW - 1) / EW, EW * 32, EW * EVD_SMEM_PER_WARP, st>>>(p, nprob, r == 0 ? 1 : 0);
+            if (!(skip & 1)) bj_gram_evd_kernel<<<dim3(lo.npairs, njobs), LT, 0, st>>>(p, r, r == 0 ? 1 : 0);
             if (!(skip & 4)) bj_apply_kernel<<<dim3(ntx + ntz, lo.npairs, njobs), LT, 0, st>>>(p, r, ntx);
         }
         bj_sweep_end_kernel<<<(njobs + 127) / 128, 128, 0, st>>>(p, njobs);
