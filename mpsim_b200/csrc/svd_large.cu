@@ -84,53 +84,74 @@ __device__ __forceinline__ void evd_rot_params(float a, float b, float gr, float
     c = (h < 0.0625f) ? fmaf(-h, poly, 1.0f) : sqrtf(fmaf(-sr, sr, fmaf(-si, si, 1.0f)));
 }
 
+// 8-byte cp.async (one complex64; always aligned) with zero fill when !valid
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, bool valid) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
+
 // One launch per round for all (job, pair) problems, a CTA of 256 threads each:
 //   1. Gram  G = Xp Xp^H  (G[i][j] = sum_c Xp[i][c] conj(Xp[j][c])): column tiles of GK staged in
-//      shared memory; the CTA is four groups of 64 threads, each group covers the whole 32 x 32
-//      output in 4 x 4 register tiles (rows ty + 8 i, tx + 8 j: conflict-free LDS, 8 LDS per
-//      64 FFMA) over its quarter of every tile; the four partial sums are added in a fixed order;
-//   2. warp 0: ONE cyclic pass of two-sided Hermitian Jacobi rotations over the pairs of the two
-//      16-row blocks (see below), G and Q in shared memory, only __syncwarp between the phases;
-//   3. all warps: one Newton-Schulz step on Q, Q to global, "rotated" flag for bj_apply_kernel.
-// (First version: three kernels -- Gram with 2 x 2 tiles, a 256-thread EVD with block-wide
-// barriers, later a warp-per-problem EVD kernel -- and a G round trip through L2.)
+//      shared memory by a two-stage cp.async ring; the CTA is four groups of 64 threads, each
+//      group covers the whole 32 x 32 output in 4 x 4 register tiles (rows ty + 8 i, tx + 8 j:
+//      conflict-free LDS, 8 LDS per 64 FFMA) over its quarter of every tile; the four partial
+//      sums are added in a fixed order;
+//   2. ONE cyclic pass of two-sided Hermitian Jacobi rotations over the pairs of the two 16-row
+//      blocks (see below), G and Q in shared memory: every warp derives the 16 rotations of a set
+//      redundantly (no exchange), then applies two of them (rows of G and Q, then columns of G);
+//   3. one Newton-Schulz step on Q, Q to global, "rotated" flag for bj_apply_kernel.
+// (First versions: three kernels -- Gram with 2 x 2 tiles, a 256-thread EVD with a converged inner
+// iteration, later a warp-per-problem EVD kernel -- and a G round trip through L2; then this kernel
+// with a single-warp pass, which left 7 of 8 warps at a barrier: profiles/r1_svd_large_ncu_full.txt.)
 constexpr int GK = 64;                       // columns per Gram tile
+constexpr int XS_LD = GK + 1;
+constexpr int GRAM_SMEM = (2 * P * XS_LD + 2 * P * (P + 1)) * (int)sizeof(cf);
 
 __global__ void __launch_bounds__(LT) bj_gram_evd_kernel(LargeParams p, int round, int first_round) {
     const int job = blockIdx.y, g = blockIdx.x;
     if (!p.misc[job].active) return;
-    __shared__ cf Xs[P][GK + 1];
-    __shared__ cf Gs[P][P + 1];
-    __shared__ cf Qs[P][P + 1];
-    __shared__ float4 prm[P / 2];            // (c, s.re, s.im, rotate?)
-    __shared__ int pidx[P / 2];              // p | q << 8
-    __shared__ int s_rot;
-    __shared__ float s_sc;
+    extern __shared__ float4 gram_smem[];
+    cf* Xbuf = reinterpret_cast<cf*>(gram_smem);
+    cf (*Gs)[P + 1] = reinterpret_cast<cf (*)[P + 1]>(Xbuf + 2 * P * XS_LD);
+    cf (*Qs)[P + 1] = Gs + P;
     int I, J;
     pair_blocks(p.nb, round, g, I, J);
     const cf* X = p.X + (size_t)job * p.x_stride;
     const int grp = threadIdx.x >> 6, t64 = threadIdx.x & 63;
     const int tx = t64 & 7, ty = t64 >> 3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    auto issue = [&](int c0, cf* buf) {
+        for (int e = threadIdx.x; e < P * GK; e += LT) {
+            const int r = e / GK, c = e % GK;
+            const bool valid = c0 + c < p.L;
+            cp_async8(&buf[r * XS_LD + c], valid ? X + (size_t)pair_row(I, J, r) * p.L + c0 + c : X, valid);
+        }
+        cp_async_commit();
+    };
     cf acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = cf_make(0.f, 0.f);
-    for (int c0 = 0; c0 < p.L; c0 += GK) {
-        for (int e = threadIdx.x; e < P * GK; e += LT) {
-            const int r = e / GK, c = e % GK;
-            Xs[r][c] = (c0 + c < p.L) ? X[(size_t)pair_row(I, J, r) * p.L + c0 + c] : cf_make(0.f, 0.f);
-        }
+    const int ntile = (p.L + GK - 1) / GK;
+    issue(0, Xbuf);
+    for (int t = 0; t < ntile; ++t) {
+        const cf* Xs = Xbuf + (t & 1) * (P * XS_LD);
+        if (t + 1 < ntile) { issue((t + 1) * GK, Xbuf + ((t + 1) & 1) * (P * XS_LD)); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
         __syncthreads();
 #pragma unroll 4
         for (int cc = 0; cc < GK / 4; ++cc) {
             const int c = grp * (GK / 4) + cc;
             cf a[4], b[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) a[i] = Xs[ty + 8 * i][c];
+            for (int i = 0; i < 4; ++i) a[i] = Xs[(ty + 8 * i) * XS_LD + c];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = Xs[tx + 8 * j][c];
+            for (int j = 0; j < 4; ++j) b[j] = Xs[(tx + 8 * j) * XS_LD + c];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -150,103 +171,118 @@ __global__ void __launch_bounds__(LT) bj_gram_evd_kernel(LargeParams p, int roun
         }
         __syncthreads();
     }
-    if (warp == 0) {
-        // scale by a power of two so that max|G| is in [1, 2)   (lane = column)
-        float mx = 0.f;
-        for (int i = 0; i < P; ++i) { cf v = Gs[i][lane]; mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))); }
+    // scale by a power of two so that max|G| is in [1, 2)   (every warp derives the same factor)
+    float mx = 0.f;
+    for (int i = 0; i < P; ++i) { cf v = Gs[i][lane]; mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))); }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        int ex = 0;
-        if (mx > 0.f && isfinite(mx)) (void)frexpf(mx, &ex);
-        const float sc = mx > 0.f ? ldexpf(1.0f, 1 - ex) : 1.0f;
-        for (int i = 0; i < P; ++i) {
-            cf v = Gs[i][lane];
-            Gs[i][lane] = cf_make(v.x * sc, v.y * sc);
-            Qs[i][lane] = cf_make(i == lane ? 1.f : 0.f, 0.f);
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    int ex = 0;
+    if (mx > 0.f && isfinite(mx)) (void)frexpf(mx, &ex);
+    const float sc = mx > 0.f ? ldexpf(1.0f, 1 - ex) : 1.0f;
+    __syncthreads();
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) {
+        const int i = warp + 8 * ii;
+        cf v = Gs[i][lane];
+        Gs[i][lane] = cf_make(v.x * sc, v.y * sc);
+        Qs[i][lane] = cf_make(i == lane ? 1.f : 0.f, 0.f);
+    }
+    __syncthreads();
+    // Rotation criterion: |G_pq| > tol sqrt(G_pp G_qq)  AND  |G_pq| > eta sigma_max max(s_p, s_q).
+    // The second (absolute) part matters for graded spectra: every GEMM that mixes a large row
+    // into a small one leaves ~eps*sigma_max of noise in it, so |G_pq| of a small pair carries
+    // noise ~eps*sigma_max*max(s_p, s_q) and the relative criterion alone is never met in fp32.
+    // A row far below sigma_max keeps a component of up to eta*sigma_max along each larger row,
+    // i.e. an absolute error of ~eta*sqrt(nv)*sigma_max in the smallest singular values: measured
+    // 6e-6 / 1.9e-5 sigma_max at nv = 512 / 2048 with eta = 1e-6, 6e-7 / 4e-6 with 2.5e-7 at the
+    // same sweep count (parity bound: 1e-5 sigma_max); eta = 3e-7 is ~5 eps.  Without
+    // preconditioning the cyclic block method converges only linearly (~2x per sweep) until then:
+    // ~10 sweeps for flat spectra, ~20 for graded ones (tests/_jacobi_model.py notes).
+    const float gmax_s = p.misc[job].gmax * sc;
+    const float eta2g = p.eta2 * gmax_s;
+    // ONE pass over the pairs of the two 16-row blocks, each rotation computed from the current
+    // (two-sidedly updated) Gram entries: the 16 cross sets (i, 16 + (i+s) mod 16), preceded in the
+    // first round of an outer sweep by the 15 intra-block sets (circle method inside each block).
+    // This is the scalar cyclic Jacobi sweep of svd_small.cu carried out on the Gram matrix: the
+    // outer iteration needs the same ~9 sweeps, but a pair step costs 16 (31) rotation sets instead
+    // of the 5 x 31 of a fully converged inner eigen-decomposition.
+    int total_rot = 0;
+    const int nsets = (first_round ? (BLK - 1) : 0) + BLK;
+    for (int t = 0; t < nsets; ++t) {
+        bool dorot = false;
+        float c = 1.f, sr = 0.f, si = 0.f;
+        int pq = 0;
+        if (lane < P / 2) {
+            int pp, qq;
+            if (first_round && t < BLK - 1) {
+                const int blk = lane >> 3, i = lane & 7, m = BLK - 1;
+                int a_, b_;
+                if (i == 0) { a_ = m; b_ = t; } else { a_ = (t + i) % m; b_ = (t - i + m) % m; }
+                pp = blk * BLK + min(a_, b_); qq = blk * BLK + max(a_, b_);
+            } else {
+                const int sft = first_round ? t - (BLK - 1) : t;
+                pp = lane; qq = BLK + ((lane + sft) & (BLK - 1));
+            }
+            const float a = Gs[pp][pp].x, b = Gs[qq][qq].x;
+            const cf gg = Gs[pp][qq];
+            const float g2 = cf_abs2(gg);
+            dorot = g2 > p.tol2 * a * b && g2 > eta2g * fmaxf(a, b) && g2 > 1e-30f;
+            if (dorot) evd_rot_params(a, b, gg.x, gg.y, g2, c, sr, si);
+            pq = pp | (qq << 8);
         }
-        __syncwarp();
-        // Rotation criterion: |G_pq| > tol sqrt(G_pp G_qq)  AND  |G_pq| > eta sigma_max max(s_p, s_q).
-        // The second (absolute) part matters for graded spectra: every GEMM that mixes a large row
-        // into a small one leaves ~eps*sigma_max of noise in it, so |G_pq| of a small pair carries
-        // noise ~eps*sigma_max*max(s_p, s_q) and the relative criterion alone is never met in fp32.
-        // A row far below sigma_max keeps a component of up to eta*sigma_max along each larger row,
-        // i.e. an absolute error of ~eta*sqrt(nv)*sigma_max ~ 8e-6 sigma_max in the smallest singular
-        // values at eta = 1e-6 (measured; parity bound: 1e-5 sigma_max).  Without preconditioning the
-        // cyclic block method converges only linearly (~2x per sweep) until then: ~10 sweeps for flat
-        // spectra, ~17 for graded ones (tests/_jacobi_model.py notes).
-        const float gmax_s = p.misc[job].gmax * sc;
-        const float eta2g = p.eta2 * gmax_s;
-        // ONE pass over the pairs of the two 16-row blocks, each rotation computed from the current
-        // (two-sidedly updated) Gram entries: the 16 cross sets (i, 16 + (i+s) mod 16), preceded in the
-        // first round of an outer sweep by the 15 intra-block sets (circle method inside each block).
-        // This is the scalar cyclic Jacobi sweep of svd_small.cu carried out on the Gram matrix: the
-        // outer iteration needs the same ~9 sweeps, but a pair step costs 16 (31) rotation sets instead
-        // of the 5 x 31 of a fully converged inner eigen-decomposition.
-        int total_rot = 0;
-        const int nsets = (first_round ? (BLK - 1) : 0) + BLK;
-        for (int t = 0; t < nsets; ++t) {
-            bool dorot = false;
-            if (lane < P / 2) {
-                int pp, qq;
-                if (first_round && t < BLK - 1) {
-                    const int blk = lane >> 3, i = lane & 7, m = BLK - 1;
-                    int a_, b_;
-                    if (i == 0) { a_ = m; b_ = t; } else { a_ = (t + i) % m; b_ = (t - i + m) % m; }
-                    pp = blk * BLK + min(a_, b_); qq = blk * BLK + max(a_, b_);
-                } else {
-                    const int sft = first_round ? t - (BLK - 1) : t;
-                    pp = lane; qq = BLK + ((lane + sft) & (BLK - 1));
-                }
-                const float a = Gs[pp][pp].x, b = Gs[qq][qq].x;
-                const cf gg = Gs[pp][qq];
-                const float g2 = cf_abs2(gg);
-                float c = 1.f, sr = 0.f, si = 0.f;
-                dorot = g2 > p.tol2 * a * b && g2 > eta2g * fmaxf(a, b) && g2 > 1e-30f;
-                if (dorot) evd_rot_params(a, b, gg.x, gg.y, g2, c, sr, si);
-                prm[lane] = make_float4(c, sr, si, dorot ? 1.f : 0.f);
-                pidx[lane] = pp | (qq << 8);
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, dorot);
-            if (bal == 0u) continue;                         // warp-uniform: nothing to rotate in this set
-            total_rot += __popc(bal);
-            __syncwarp();
-            // rows: [g_p; g_q] <- J [g_p; g_q], same for Q      (lane = column)
-#pragma unroll 4
-            for (int i = 0; i < P / 2; ++i) {
-                if (!((bal >> i) & 1u)) continue;
-                const float4 pr = prm[i];
-                const int ip = pidx[i] & 0xff, iq = pidx[i] >> 8;
-                cf x = Gs[ip][lane], y = Gs[iq][lane];
-                cf nx, ny;
-                nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, -(pr.z * y.y)));
-                nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, pr.z * y.x));
-                ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, pr.z * x.y));
-                ny.y = fmaf(pr.x, y.y, fmaf(pr.z, x.x, -(pr.y * x.y)));
-                Gs[ip][lane] = nx; Gs[iq][lane] = ny;
-                x = Qs[ip][lane]; y = Qs[iq][lane];
-                nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, -(pr.z * y.y)));
-                nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, pr.z * y.x));
-                ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, pr.z * x.y));
-                ny.y = fmaf(pr.x, y.y, fmaf(pr.z, x.x, -(pr.y * x.y)));
-                Qs[ip][lane] = nx; Qs[iq][lane] = ny;
-            }
-            __syncwarp();
-            // columns: [g_.p, g_.q] <- [g_.p, g_.q] J^H :  p' = c p + conj(s) q ; q' = -s p + c q   (lane = row)
-#pragma unroll 4
-            for (int i = 0; i < P / 2; ++i) {
-                if (!((bal >> i) & 1u)) continue;
-                const float4 pr = prm[i];
-                const int ip = pidx[i] & 0xff, iq = pidx[i] >> 8;
-                const cf x = Gs[lane][ip], y = Gs[lane][iq];
-                cf nx, ny;
-                nx.x = fmaf(pr.x, x.x, fmaf(pr.y, y.x, pr.z * y.y));
-                nx.y = fmaf(pr.x, x.y, fmaf(pr.y, y.y, -(pr.z * y.x)));
-                ny.x = fmaf(pr.x, y.x, -fmaf(pr.y, x.x, -(pr.z * x.y)));
-                ny.y = fmaf(pr.x, y.y, -fmaf(pr.y, x.y, pr.z * x.x));
-                Gs[lane][ip] = nx; Gs[lane][iq] = ny;
-            }
-            __syncwarp();
+        const unsigned bal = __ballot_sync(0xffffffffu, dorot);
+        if (bal == 0u) continue;                 // identical in every warp: nothing to rotate in this set
+        total_rot += __popc(bal);
+        __syncthreads();                         // all warps have read G for their parameters
+        // this warp's two rotations of the set
+        float rc[2], rsr[2], rsi[2];
+        int rpq[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const int src = 2 * warp + u;
+            rc[u] = __shfl_sync(0xffffffffu, c, src);
+            rsr[u] = __shfl_sync(0xffffffffu, sr, src);
+            rsi[u] = __shfl_sync(0xffffffffu, si, src);
+            rpq[u] = __shfl_sync(0xffffffffu, pq, src);
         }
+        // rows: [g_p; g_q] <- J [g_p; g_q], same for Q      (lane = column)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!((bal >> (2 * warp + u)) & 1u)) continue;
+            const int ip = rpq[u] & 0xff, iq = rpq[u] >> 8;
+            const float pc = rc[u], ps = rsr[u], pi = rsi[u];
+            cf x = Gs[ip][lane], y = Gs[iq][lane];
+            cf nx, ny;
+            nx.x = fmaf(pc, x.x, fmaf(ps, y.x, -(pi * y.y)));
+            nx.y = fmaf(pc, x.y, fmaf(ps, y.y, pi * y.x));
+            ny.x = fmaf(pc, y.x, -fmaf(ps, x.x, pi * x.y));
+            ny.y = fmaf(pc, y.y, fmaf(pi, x.x, -(ps * x.y)));
+            Gs[ip][lane] = nx; Gs[iq][lane] = ny;
+            x = Qs[ip][lane]; y = Qs[iq][lane];
+            nx.x = fmaf(pc, x.x, fmaf(ps, y.x, -(pi * y.y)));
+            nx.y = fmaf(pc, x.y, fmaf(ps, y.y, pi * y.x));
+            ny.x = fmaf(pc, y.x, -fmaf(ps, x.x, pi * x.y));
+            ny.y = fmaf(pc, y.y, fmaf(pi, x.x, -(ps * x.y)));
+            Qs[ip][lane] = nx; Qs[iq][lane] = ny;
+        }
+        __syncthreads();
+        // columns: [g_.p, g_.q] <- [g_.p, g_.q] J^H :  p' = c p + conj(s) q ; q' = -s p + c q   (lane = row)
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            if (!((bal >> (2 * warp + u)) & 1u)) continue;
+            const int ip = rpq[u] & 0xff, iq = rpq[u] >> 8;
+            const float pc = rc[u], ps = rsr[u], pi = rsi[u];
+            const cf x = Gs[lane][ip], y = Gs[lane][iq];
+            cf nx, ny;
+            nx.x = fmaf(pc, x.x, fmaf(ps, y.x, pi * y.y));
+            nx.y = fmaf(pc, x.y, fmaf(ps, y.y, -(pi * y.x)));
+            ny.x = fmaf(pc, y.x, -fmaf(ps, x.x, -(pi * x.y)));
+            ny.y = fmaf(pc, y.y, -fmaf(ps, x.y, pi * x.x));
+            Gs[lane][ip] = nx; Gs[lane][iq] = ny;
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {
         float lam = Gs[lane][lane].x;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) lam = fmaxf(lam, __shfl_xor_sync(0xffffffffu, lam, o));
@@ -254,11 +290,10 @@ __global__ void __launch_bounds__(LT) bj_gram_evd_kernel(LargeParams p, int roun
             atomicMax(&p.misc[job].gmax_next, __float_as_uint(fmaxf(lam, 0.f) / sc));
             if (total_rot > 0) atomicAdd(&p.misc[job].rot, 1);
             p.rotflag[(size_t)job * p.npairs + g] = total_rot > 0 ? 1 : 0;
-            s_rot = total_rot;
         }
     }
-    __syncthreads();
-    if (s_rot == 0) return;                  // Q = I: bj_apply_kernel skips this pair
+    if (total_rot == 0) return;              // Q = I: bj_apply_kernel skips this pair (same count in every warp)
+    __syncthreads();                         // lam has been read before R overwrites G
     // Q is written UNSORTED: small-angle rotations started from the identity keep Q close to
     // the identity, which the cyclic block method needs to converge (sorting the rows by
     // eigenvalue is a permutation far from the identity and makes the outer iteration cycle).
@@ -300,52 +335,79 @@ __global__ void __launch_bounds__(LT) bj_gram_evd_kernel(LargeParams p, int roun
     }
 }
 
-// rows of the pair, columns [c0, c0+CT) of [X | Z]:  T <- Q T   (in place).  A thread owns two
-// columns (c, c + CT/2) and 8 of the 32 output rows: per k two LDS.64 of T and four broadcast
-// LDS.128 of Q^T for 64 FFMA (the first version had one column per thread: 9 LDS per 32 FFMA).
-__global__ void __launch_bounds__(LT) bj_apply_kernel(LargeParams p, int round, int ntx) {
-    const int job = blockIdx.z, g = blockIdx.y, tile = blockIdx.x;
+// rows of the pair, columns of [X | Z]:  T <- Q T   (in place).  A CTA walks NT_APPLY column
+// tiles of CT columns with a two-stage cp.async ring (the loads of tile t+1 overlap the FFMAs of
+// tile t; the first version loaded, synchronised, computed and stored one tile per CTA and spent
+// its time on the long scoreboard: FMA pipe 39 % -- profiles/r1_svd_large_ncu_full.txt).  A thread
+// owns two columns (c, c + CT/2) and 8 of the 32 output rows: per k two LDS.64 of T and four
+// broadcast LDS.128 of Q^T for 64 FFMA.
+constexpr int NT_APPLY = 4;
+constexpr int TS_LD = CT + 2;                                 // row stride of a staged tile (elements)
+constexpr int APPLY_SMEM = (P * (P + 2) + 2 * P * TS_LD) * (int)sizeof(cf);
+
+__global__ void __launch_bounds__(LT) bj_apply_kernel(LargeParams p, int round, int ntx, int ntot) {
+    const int job = blockIdx.z, g = blockIdx.y;
     if (!p.misc[job].active) return;
     if (!p.rotflag[(size_t)job * p.npairs + g]) return;      // no rotation in this pair: Q = I
-    __shared__ __align__(16) cf Qt[P][P + 2];                // Qt[k][i] = Q[i][k]  (+2: 4-way instead of 32-way store conflicts)
-    __shared__ cf Ts[P][CT + 1];
+    extern __shared__ float4 apply_smem[];
+    cf (*Qt)[P + 2] = reinterpret_cast<cf (*)[P + 2]>(apply_smem);          // Qt[k][i] = Q[i][k]
+    cf* Tbuf = reinterpret_cast<cf*>(apply_smem) + P * (P + 2);
     int I, J;
     pair_blocks(p.nb, round, g, I, J);
-    cf* base; int ld, c0, ncol;
-    if (tile < ntx) { base = p.X + (size_t)job * p.x_stride; ld = p.L; c0 = tile * CT; ncol = p.L; }
-    else { base = p.Z + (size_t)job * p.z_stride; ld = p.nvp; c0 = (tile - ntx) * CT; ncol = p.nvp; }
+    const int tile0 = blockIdx.x * NT_APPLY;
+    const int nt = min(NT_APPLY, ntot - tile0);
+    cf* const Xb = p.X + (size_t)job * p.x_stride;
+    cf* const Zb = p.Z + (size_t)job * p.z_stride;
+    auto issue = [&](int tile, cf* buf) {
+        cf* base; int ld, c0, ncol;
+        if (tile < ntx) { base = Xb; ld = p.L; c0 = tile * CT; ncol = p.L; }
+        else { base = Zb; ld = p.nvp; c0 = (tile - ntx) * CT; ncol = p.nvp; }
+        for (int e = threadIdx.x; e < P * CT; e += LT) {
+            const int r = e / CT, c = e - r * CT;
+            const bool valid = c0 + c < ncol;
+            cp_async8(&buf[r * TS_LD + c], valid ? base + (size_t)pair_row(I, J, r) * ld + c0 + c : base, valid);
+        }
+        cp_async_commit();
+    };
+    issue(tile0, Tbuf);
     const cf* Q = p.Q + (size_t)job * p.g_stride + (size_t)g * P * P;
     for (int e = threadIdx.x; e < P * P; e += LT) Qt[e % P][e / P] = Q[e];
-    for (int e = threadIdx.x; e < P * CT; e += LT) {
-        int r = e / CT, c = e - r * CT;
-        Ts[r][c] = (c0 + c < ncol) ? base[(size_t)pair_row(I, J, r) * ld + c0 + c] : cf_make(0.f, 0.f);
-    }
-    __syncthreads();
     constexpr int HC = CT / 2;                               // 64 column pairs x 4 row groups
     const int c = threadIdx.x % HC, rg = threadIdx.x / HC;
     constexpr int RPT = P / (LT / HC);                       // 8 rows per thread
-    cf acc0[RPT], acc1[RPT];
+    for (int t = 0; t < nt; ++t) {
+        const cf* Ts = Tbuf + (t & 1) * (P * TS_LD);
+        if (t + 1 < nt) { issue(tile0 + t + 1, Tbuf + ((t + 1) & 1) * (P * TS_LD)); cp_async_wait<1>(); }
+        else cp_async_wait<0>();
+        __syncthreads();
+        cf acc0[RPT], acc1[RPT];
 #pragma unroll
-    for (int i = 0; i < RPT; ++i) { acc0[i] = cf_make(0.f, 0.f); acc1[i] = cf_make(0.f, 0.f); }
+        for (int i = 0; i < RPT; ++i) { acc0[i] = cf_make(0.f, 0.f); acc1[i] = cf_make(0.f, 0.f); }
 #pragma unroll 4
-    for (int k = 0; k < P; ++k) {
-        const cf t0 = Ts[k][c], t1 = Ts[k][c + HC];
-        const float4* qrow = reinterpret_cast<const float4*>(&Qt[k][rg * RPT]);
+        for (int k = 0; k < P; ++k) {
+            const cf t0 = Ts[k * TS_LD + c], t1 = Ts[k * TS_LD + c + HC];
+            const float4* qrow = reinterpret_cast<const float4*>(&Qt[k][rg * RPT]);
 #pragma unroll
-        for (int i2 = 0; i2 < RPT / 2; ++i2) {
-            const float4 q2 = qrow[i2];
-            const cf qa = cf_make(q2.x, q2.y), qb = cf_make(q2.z, q2.w);
-            acc0[2 * i2] = cf_fma(qa, t0, acc0[2 * i2]);
-            acc1[2 * i2] = cf_fma(qa, t1, acc1[2 * i2]);
-            acc0[2 * i2 + 1] = cf_fma(qb, t0, acc0[2 * i2 + 1]);
-            acc1[2 * i2 + 1] = cf_fma(qb, t1, acc1[2 * i2 + 1]);
+            for (int i2 = 0; i2 < RPT / 2; ++i2) {
+                const float4 q2 = qrow[i2];
+                const cf qa = cf_make(q2.x, q2.y), qb = cf_make(q2.z, q2.w);
+                acc0[2 * i2] = cf_fma(qa, t0, acc0[2 * i2]);
+                acc1[2 * i2] = cf_fma(qa, t1, acc1[2 * i2]);
+                acc0[2 * i2 + 1] = cf_fma(qb, t0, acc0[2 * i2 + 1]);
+                acc1[2 * i2 + 1] = cf_fma(qb, t1, acc1[2 * i2 + 1]);
+            }
         }
-    }
+        const int tile = tile0 + t;
+        cf* base; int ld, c0, ncol;
+        if (tile < ntx) { base = Xb; ld = p.L; c0 = tile * CT; ncol = p.L; }
+        else { base = Zb; ld = p.nvp; c0 = (tile - ntx) * CT; ncol = p.nvp; }
 #pragma unroll
-    for (int i = 0; i < RPT; ++i) {
-        cf* row = base + (size_t)pair_row(I, J, rg * RPT + i) * ld + c0;
-        if (c0 + c < ncol) row[c] = acc0[i];
-        if (c0 + c + HC < ncol) row[c + HC] = acc1[i];
+        for (int i = 0; i < RPT; ++i) {
+            cf* row = base + (size_t)pair_row(I, J, rg * RPT + i) * ld + c0;
+            if (c0 + c < ncol) row[c] = acc0[i];
+            if (c0 + c + HC < ncol) row[c + HC] = acc1[i];
+        }
+        __syncthreads();                                     // the other stage is refilled next iteration
     }
 }
 
@@ -502,6 +564,8 @@ int launch_svd_large(cf* X, int64_t x_job_stride, int njobs, int nv, int L, int 
     MPSB_LAUNCH_CHECK("bj_init_kernel");
     const int nrounds = lo.nb > 2 ? lo.nb - 1 : 1;
     const int ntx = (L + CT - 1) / CT, ntz = (lo.nvp + CT - 1) / CT;
+    MPSB_CUDA(cudaFuncSetAttribute(bj_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, APPLY_SMEM));
+    MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM));
     int skip = 0, max_outer = MAX_OUTER;         // timing experiments only
     if (const char* e = getenv("MPSB_LARGE_SKIP")) skip = atoi(e);
     if (const char* e = getenv("MPSB_LARGE_SWEEPS")) max_outer = atoi(e);
@@ -524,8 +588,9 @@ int launch_svd_large(cf* X, int64_t x_job_stride, int njobs, int nv, int L, int 
     int pending = -1, slot = 0;
     for (int sweep = 0; sweep < max_outer; ++sweep) {
         for (int r = 0; r < nrounds; ++r) {
-            if (!(skip & 1)) bj_gram_evd_kernel<<<dim3(lo.npairs, njobs), LT, 0, st>>>(p, r, r == 0 ? 1 : 0);
-            if (!(skip & 4)) bj_apply_kernel<<<dim3(ntx + ntz, lo.npairs, njobs), LT, 0, st>>>(p, r, ntx);
+            if (!(skip & 1)) bj_gram_evd_kernel<<<dim3(lo.npairs, njobs), LT, GRAM_SMEM, st>>>(p, r, r == 0 ? 1 : 0);
+            if (!(skip & 4))
+                bj_apply_kernel<<<dim3((ntx + ntz + NT_APPLY - 1) / NT_APPLY, lo.npairs, njobs), LT, APPLY_SMEM, st>>>(p, r, ntx, ntx + ntz);
         }
         bj_sweep_end_kernel<<<(njobs + 127) / 128, 128, 0, st>>>(p, njobs);
         if (sweep >= 3 && (sweep & 1) && sweep + 1 < max_outer) {
