@@ -78,6 +78,23 @@ int mpsb_apply_gate2(const mpsb_gate2_desc* descs_dev, int ndesc, int nbatch,
                      int d, int chiL, int chiM, int chiR, int k, int left_canonical,
                      void* workspace, size_t workspace_bytes, int32_t* info, void* stream);
 
+/* One shape class of a circuit layer: the arguments of one mpsb_apply_gate2 call. */
+typedef struct mpsb_gate2_group {
+    const mpsb_gate2_desc* descs_dev;   /* this group's descriptors (device memory) */
+    int32_t* info;                      /* device int32 [ndesc*nbatch][2], or NULL */
+    int32_t ndesc, chiL, chiM, chiR, k, left_canonical;
+} mpsb_gate2_group;
+
+/* All shape classes of ONE layer of disjoint applications (the moment dispatcher's unit,
+ * core.py:1221-1247 "TODO: Parallelize") in one call: same result as ngroups mpsb_apply_gate2
+ * calls, but the groups run concurrently on library-owned streams forked from / joined to
+ * `stream` -- a group of one or two large matrices is latency bound and hides behind the
+ * layer's main group.  groups_host is read on the host during the call.  Workspace:
+ * mpsb_gate2_layer_workspace_bytes() (the groups' own needs, 256-byte aligned, summed). */
+size_t mpsb_gate2_layer_workspace_bytes(const mpsb_gate2_group* groups_host, int ngroups, int nbatch, int d);
+int mpsb_apply_gate2_layer(const mpsb_gate2_group* groups_host, int ngroups, int nbatch, int d,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* A'[l,o,r] = sum_p g[o,p] A[l,p,r] for ndesc*nbatch sites (core.py:819-826). */
 int mpsb_apply_gate1(const mpsb_gate1_desc* descs_dev, int ndesc, int nbatch, int d,
                      int max_site_elems, void* stream);

@@ -13,6 +13,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmpsim_b200.so")
 
+MAX_SMALL_DIM = 128      # MPSB_MAX_SMALL_DIM of include/mpsim_b200.h
+
 c_void_p, c_int, c_size_t, c_int64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_int64
 
 # numpy mirrors of the descriptor structs (same field order / padding as the C header)
@@ -27,8 +29,11 @@ GATE1_DESC = np.dtype([
     ("bs_site", np.int64), ("bs_out", np.int64), ("bs_gate", np.int64),
     ("chiL", np.int32), ("chiR", np.int32),
 ], align=True)
+GATE2_GROUP = np.dtype([("descs", np.uint64), ("info", np.uint64), ("ndesc", np.int32), ("chiL", np.int32),
+                        ("chiM", np.int32), ("chiR", np.int32), ("k", np.int32), ("left_canonical", np.int32)], align=True)
 SITE_REF = np.dtype([("site", np.uint64), ("bs", np.int64), ("chiL", np.int32), ("chiR", np.int32)], align=True)
 assert GATE2_DESC.itemsize == 96 and GATE1_DESC.itemsize == 56 and SITE_REF.itemsize == 24
+assert GATE2_GROUP.itemsize == 40
 
 #: every symbol include/mpsim_b200.h declares: name -> (restype, argtypes)
 SYMBOLS = {
@@ -38,6 +43,8 @@ SYMBOLS = {
     "mpsb_gate2_workspace_bytes": (c_size_t, [c_int] * 7),
     "mpsb_apply_gate2": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
                                  c_void_p, c_size_t, c_void_p, c_void_p]),
+    "mpsb_gate2_layer_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int, c_int]),
+    "mpsb_apply_gate2_layer": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "mpsb_apply_gate1": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "mpsb_inner_workspace_bytes": (c_size_t, [c_int] * 4),
     "mpsb_inner_products": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

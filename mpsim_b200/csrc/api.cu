@@ -3,6 +3,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <string>
+#include <vector>
 
 int launch_gate1(const mpsb_gate1_desc* descs, int ndesc, int nbatch, int d, int max_site_elems, cudaStream_t st);
 int launch_scale(const mpsb_site_ref* sites, int nsites, int nbatch, int d, const float* factors,
@@ -99,37 +100,45 @@ size_t mpsb_gate2_workspace_bytes(int ndesc, int nbatch, int d, int chiL, int ch
     return (a > b ? a : b) * sizeof(cf) * (size_t)ndesc * nbatch + 256 + tc;
 }
 
-int mpsb_apply_gate2(const mpsb_gate2_desc* descs_dev, int ndesc, int nbatch,
-                     int d, int chiL, int chiM, int chiR, int k, int left_canonical,
-                     void* workspace, size_t workspace_bytes, int32_t* info, void* stream) {
-    cudaStream_t st = (cudaStream_t)stream;
+// theta of one shape group onto `st`; returns the plan and where X / the SVD scratch live
+static int gate2_theta(const mpsb_gate2_desc* descs_dev, int ndesc, int nbatch, int d, int chiL, int chiM, int chiR,
+                       int k, int left_canonical, void* workspace, size_t workspace_bytes, cudaStream_t st,
+                       Gate2Plan& p, cf*& X, cf*& extra) {
     MPSB_ARG(descs_dev != nullptr, "apply_gate2: descs is NULL");
     MPSB_ARG(ndesc >= 0 && nbatch >= 0, "apply_gate2: negative counts");
     MPSB_ARG(d >= 2, "apply_gate2: qudit dimension %d < 2", d);
     MPSB_ARG(chiL >= 0 && chiM >= 0 && chiR >= 0, "apply_gate2: negative bond dimension");
     int njobs = ndesc * nbatch;
-    if (njobs == 0 || chiL == 0 || chiR == 0) return 0;   // empty tensors: nothing to compute
     int mn = d * (chiL < chiR ? chiL : chiR);
     // k == 0 is legal (maxsvals=0, core_test.py:1093-1101): the sites become empty but the
     // singular values are still computed and reported
     MPSB_ARG(k >= 0 && k <= mn, "apply_gate2: k=%d outside [0, %d]", k, mn);
     MPSB_ARG(njobs <= 65535, "apply_gate2: %d applications in one call (max 65535); split the call", njobs);
-    Gate2Plan p = plan_gate2(d, chiL, chiR, left_canonical ? 1 : 0);
+    p = plan_gate2(d, chiL, chiR, left_canonical ? 1 : 0);
     const bool tc = theta_uses_tc(d, chiL, chiM, chiR);
     size_t need_svd = align_up(p.job_elems * sizeof(cf) * (size_t)njobs, 256);
     size_t need = need_svd + (tc ? tc_theta_workspace_floats(njobs, chiL, chiM, chiR) * sizeof(float) : 0);
     MPSB_ARG(workspace != nullptr && workspace_bytes >= need, "apply_gate2: workspace %zu B < %zu B", workspace_bytes, need);
     MPSB_ARG(((uintptr_t)workspace & 255) == 0, "apply_gate2: workspace must be 256-byte aligned");
     cf* ws = (cf*)workspace;
-    cf* X = ws;                                              // [njobs][x_elems]
-    cf* extra = ws + align_up(p.x_elems, 16) * (size_t)njobs;     // [njobs][extra]
-    int rc;
+    X = ws;                                                  // [njobs][x_elems]
+    extra = ws + align_up(p.x_elems, 16) * (size_t)njobs;    // [njobs][extra]
     if (tc)
-        rc = launch_theta_tc(descs_dev, ndesc, nbatch, chiL, chiM, chiR, left_canonical ? 0 : 1, X,
-                             (int64_t)align_up(p.x_elems, 16), (float*)((char*)workspace + need_svd), st);
-    else
-        rc = launch_theta(descs_dev, ndesc, nbatch, d, chiL, chiM, chiR, left_canonical ? 0 : 1,
-                          X, (int64_t)align_up(p.x_elems, 16), st);
+        return launch_theta_tc(descs_dev, ndesc, nbatch, chiL, chiM, chiR, left_canonical ? 0 : 1, X,
+                               (int64_t)align_up(p.x_elems, 16), (float*)((char*)workspace + need_svd), st);
+    return launch_theta(descs_dev, ndesc, nbatch, d, chiL, chiM, chiR, left_canonical ? 0 : 1,
+                        X, (int64_t)align_up(p.x_elems, 16), st);
+}
+
+int mpsb_apply_gate2(const mpsb_gate2_desc* descs_dev, int ndesc, int nbatch,
+                     int d, int chiL, int chiM, int chiR, int k, int left_canonical,
+                     void* workspace, size_t workspace_bytes, int32_t* info, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    int njobs = ndesc * nbatch;
+    if (njobs == 0 || chiL == 0 || chiR == 0) return 0;   // empty tensors: nothing to compute
+    Gate2Plan p; cf *X, *extra;
+    int rc = gate2_theta(descs_dev, ndesc, nbatch, d, chiL, chiM, chiR, k, left_canonical, workspace, workspace_bytes, st,
+                         p, X, extra);
     if (rc) return rc;
     if (p.small) {
         return launch_svd_small(X, (int64_t)align_up(p.x_elems, 16), njobs, p.nv, p.L, k, left_canonical ? 1 : 0,
@@ -138,6 +147,99 @@ int mpsb_apply_gate2(const mpsb_gate2_desc* descs_dev, int ndesc, int nbatch,
     }
     return launch_svd_large(X, (int64_t)align_up(p.x_elems, 16), njobs, p.nv, p.L, k, left_canonical ? 1 : 0,
                             descs_dev, ndesc, nbatch, nullptr, 0, nullptr, 0, nullptr, 0, info, extra, st);
+}
+
+size_t mpsb_gate2_layer_workspace_bytes(const mpsb_gate2_group* g, int ngroups, int nbatch, int d) {
+    size_t tot = 0;
+    for (int i = 0; i < ngroups; ++i)
+        tot += align_up(mpsb_gate2_workspace_bytes(g[i].ndesc, nbatch, d, g[i].chiL, g[i].chiM, g[i].chiR, g[i].k), 256);
+    return tot;
+}
+
+// library-owned streams of mpsb_apply_gate2_layer (created once; never destroyed)
+static const int kPoolStreams = 8;
+static cudaStream_t g_pool[kPoolStreams];
+static cudaEvent_t g_fork = nullptr, g_join[kPoolStreams];
+static bool g_pool_ready = false;
+
+int mpsb_apply_gate2_layer(const mpsb_gate2_group* groups, int ngroups, int nbatch, int d,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    MPSB_ARG(groups != nullptr || ngroups == 0, "apply_gate2_layer: groups is NULL");
+    MPSB_ARG(ngroups >= 0 && ngroups <= 4096, "apply_gate2_layer: %d groups", ngroups);
+    if (ngroups == 0 || nbatch == 0) return 0;
+    MPSB_ARG(workspace_bytes >= mpsb_gate2_layer_workspace_bytes(groups, ngroups, nbatch, d),
+             "apply_gate2_layer: workspace too small");
+    if (!g_pool_ready) {
+        for (int i = 0; i < kPoolStreams; ++i) {
+            MPSB_CUDA(cudaStreamCreateWithFlags(&g_pool[i], cudaStreamNonBlocking));
+            MPSB_CUDA(cudaEventCreateWithFlags(&g_join[i], cudaEventDisableTiming));
+        }
+        MPSB_CUDA(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
+        g_pool_ready = true;
+    }
+    // heaviest group first: it stays on the caller's stream, the others go round the pool
+    std::vector<int> order(ngroups);
+    std::vector<double> cost(ngroups);
+    std::vector<size_t> offs(ngroups);
+    size_t off = 0;
+    for (int i = 0; i < ngroups; ++i) {
+        order[i] = i;
+        double mx = (double)d * (groups[i].chiL > groups[i].chiR ? groups[i].chiL : groups[i].chiR);
+        cost[i] = (double)groups[i].ndesc * nbatch * mx * mx * mx;
+        offs[i] = off;
+        off += align_up(mpsb_gate2_workspace_bytes(groups[i].ndesc, nbatch, d, groups[i].chiL, groups[i].chiM,
+                                                   groups[i].chiR, groups[i].k), 256);
+    }
+    for (int a = 1; a < ngroups; ++a)                        // insertion sort, descending cost
+        for (int b = a; b > 0 && cost[order[b]] > cost[order[b - 1]]; --b) { int t = order[b]; order[b] = order[b - 1]; order[b - 1] = t; }
+    if (ngroups > 1) {
+        MPSB_CUDA(cudaEventRecord(g_fork, st));
+        for (int i = 0; i < kPoolStreams && i < ngroups - 1; ++i) MPSB_CUDA(cudaStreamWaitEvent(g_pool[i], g_fork, 0));
+    }
+    std::vector<LargeMultiJob> large;
+    int rc = 0;
+    auto flush_large = [&]() -> int {
+        if (large.empty()) return 0;
+        int r = launch_svd_large_multi(large.data(), (int)large.size());
+        large.clear();
+        return r;
+    };
+    for (int oi = 0; oi < ngroups && rc == 0; ++oi) {
+        const mpsb_gate2_group& g = groups[order[oi]];
+        const int njobs = g.ndesc * nbatch;
+        if (njobs == 0 || g.chiL == 0 || g.chiR == 0) continue;
+        const int slot = oi == 0 ? kPoolStreams : (oi - 1) % kPoolStreams;     // pin slot == stream index
+        cudaStream_t gs = oi == 0 ? st : g_pool[slot];
+        char* ws = (char*)workspace + offs[order[oi]];
+        size_t wsb = mpsb_gate2_workspace_bytes(g.ndesc, nbatch, d, g.chiL, g.chiM, g.chiR, g.k);
+        Gate2Plan p; cf *X, *extra;
+        rc = gate2_theta(g.descs_dev, g.ndesc, nbatch, d, g.chiL, g.chiM, g.chiR, g.k, g.left_canonical, ws, wsb, gs, p, X, extra);
+        if (rc) break;
+        if (p.small) {
+            rc = launch_svd_small(X, (int64_t)align_up(p.x_elems, 16), njobs, p.nv, p.L, g.k, g.left_canonical ? 1 : 0,
+                                  g.descs_dev, g.ndesc, nbatch, nullptr, 0, nullptr, 0, nullptr, 0, g.info,
+                                  p.extra_elems ? extra : nullptr, gs);
+            continue;
+        }
+        // a stream (and its pinned read-back slot) carries one large solve at a time
+        for (const LargeMultiJob& j : large)
+            if (j.pin_slot == slot) { rc = flush_large(); break; }
+        if (rc) break;
+        LargeMultiJob j;
+        j.X = X; j.x_job_stride = (int64_t)align_up(p.x_elems, 16); j.njobs = njobs; j.nv = p.nv; j.L = p.L; j.k = g.k;
+        j.left_canonical = g.left_canonical ? 1 : 0; j.descs = g.descs_dev; j.nbatch = nbatch; j.info = g.info;
+        j.work = extra; j.st = gs; j.pin_slot = slot;
+        large.push_back(j);
+    }
+    if (rc == 0) rc = flush_large();
+    if (ngroups > 1) {                                       // join even after an error: never leave the pool detached
+        for (int i = 0; i < kPoolStreams && i < ngroups - 1; ++i) {
+            cudaEventRecord(g_join[i], g_pool[i]);
+            cudaStreamWaitEvent(st, g_join[i], 0);
+        }
+    }
+    return rc;
 }
 
 int mpsb_apply_gate1(const mpsb_gate1_desc* descs_dev, int ndesc, int nbatch, int d,

@@ -91,6 +91,12 @@ int launch_svd_small(const cf* X, int64_t x_job_stride, int njobs, int nv, int L
                      float* svals, int64_t svals_stride, int32_t* info, cf* zglobal,
                      cudaStream_t st);
 size_t svd_large_workspace_elems(int nv, int L);
+// one shape group of a multi-stream large-SVD call (svd_large.cu: launch_svd_large_multi)
+struct LargeMultiJob {
+    cf* X; int64_t x_job_stride; int njobs, nv, L, k, left_canonical;
+    const mpsb_gate2_desc* descs; int nbatch; int32_t* info; cf* work; cudaStream_t st; int pin_slot;
+};
+int launch_svd_large_multi(const LargeMultiJob* jobs, int n);
 int svd_large_padded_rows(int nv);
 int launch_svd_large(cf* X, int64_t x_job_stride, int njobs, int nv, int L, int k,
                      int left_canonical, const mpsb_gate2_desc* descs, int ndesc, int nbatch,

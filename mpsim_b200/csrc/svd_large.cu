@@ -15,6 +15,7 @@
 #include "common.cuh"
 #include <vector>
 #include <stdlib.h>
+#include <sched.h>
 
 namespace {
 
@@ -517,6 +518,184 @@ LargeLayout large_layout(int nv, int L) {
     return lo;
 }
 
+// ---------------------------------------------------------------------------------------
+// Host driver.  A solve is a resumable object (LargeRun): begin -> enqueue sweeps -> finish, so
+// that several shape groups of one circuit layer can be in flight on different streams at once
+// (mpsb_apply_gate2_layer): a group of one or two matrices is bound by the latency of its ~600
+// dependent rounds (~27 us each), not by throughput, and hides completely behind the layer's
+// main group.  Convergence is read back without ever blocking a stream: every CHECK_EVERY sweeps
+// the per-job flags are copied to pinned host memory behind an event; the host polls the events
+// and keeps up to MAX_CHECKS checks (sweeps already queued behind them) outstanding per run.
+// ---------------------------------------------------------------------------------------
+constexpr int CHECK_EVERY = 2;
+constexpr int MAX_CHECKS = 2;
+constexpr int PIN_SLOTS = 9;                 // 8 pool streams + the caller's stream
+
+struct PinSlot {
+    Misc* host = nullptr;                    // [MAX_CHECKS][jobs_cap]
+    size_t jobs_cap = 0;
+    cudaEvent_t ev[MAX_CHECKS] = {nullptr, nullptr};
+};
+static PinSlot g_pin[PIN_SLOTS];
+
+struct LargeRun {
+    LargeParams p;
+    LargeLayout lo;
+    OutParams o;
+    cf *Rbuf, *Z2, *M0;
+    int njobs, nv, L, nrounds, ntx, ntz, max_outer, skip;
+    cudaStream_t st;
+    PinSlot* pin;
+    int sweeps_queued = 0;
+    int checks_out = 0, check_head = 0;      // ring of outstanding checks
+    bool done = false;
+};
+
+static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int nv, int L, int k,
+                       int left_canonical, const mpsb_gate2_desc* descs, int nbatch,
+                       cf* left, int64_t left_stride, cf* right, int64_t right_stride,
+                       float* svals, int64_t svals_stride, int32_t* info, cf* work,
+                       cudaStream_t st, int pin_slot) {
+    MPSB_ARG(work != nullptr, "svd_large: workspace missing");
+    MPSB_ARG(njobs <= 65535, "svd_large: njobs %d > 65535", njobs);
+    MPSB_ARG(pin_slot >= 0 && pin_slot < PIN_SLOTS, "svd_large: bad pin slot");
+    LargeLayout lo = large_layout(nv, L);
+    MPSB_ARG(x_job_stride >= (int64_t)lo.nvp * L, "svd_large: X stride too small for the padded rows");
+    LargeParams& p = r.p;
+    p.X = X; p.x_stride = x_job_stride;
+    // workspace: [njobs][Z] [njobs][flags] [njobs][Q] [njobs][sigma|perm] [njobs][misc] R Z2 M0
+    cf* w = work;
+    p.Z = w; p.z_stride = (int64_t)lo.z; w += lo.z * njobs;
+    p.rotflag = (int*)w; w += lo.g * njobs;          // (region of the former G buffer)
+    p.Q = w; w += lo.g * njobs;
+    p.g_stride = (int64_t)lo.g;
+    p.sigma = (float*)w; p.perm = (int*)((float*)w + (size_t)lo.s * njobs); p.s_stride = (int64_t)lo.s; w += lo.s * njobs;
+    p.misc = (Misc*)w; w += lo.misc * njobs;
+    r.Rbuf = w; w += lo.z * njobs;
+    r.Z2 = w; w += lo.z * njobs;
+    r.M0 = w;
+    p.nv = nv; p.L = L; p.nvp = lo.nvp; p.nb = lo.nb; p.npairs = lo.npairs;
+    // the Gram entries carry rounding noise ~ eps*sqrt(L)*sqrt(G_ii G_jj): keep the threshold above it
+    float tol = 3e-6f;
+    float floor_ = 4.0f * 5.96e-8f * sqrtf((float)L);
+    if (floor_ > tol) tol = floor_;
+    p.tol2 = tol * tol;
+    float eta = ABS_ETA;
+    if (const char* e = getenv("MPSB_LARGE_ETA")) eta = (float)atof(e);          // experiments only
+    p.eta2 = eta * eta;
+    r.lo = lo; r.njobs = njobs; r.nv = nv; r.L = L; r.st = st;
+    r.nrounds = lo.nb > 2 ? lo.nb - 1 : 1;
+    r.ntx = (L + CT - 1) / CT; r.ntz = (lo.nvp + CT - 1) / CT;
+    r.skip = 0; r.max_outer = MAX_OUTER;          // timing experiments only
+    if (const char* e = getenv("MPSB_LARGE_SKIP")) r.skip = atoi(e);
+    if (const char* e = getenv("MPSB_LARGE_SWEEPS")) r.max_outer = atoi(e);
+    OutParams& o = r.o;
+    o.descs = descs; o.nbatch = nbatch > 0 ? nbatch : 1;
+    o.left = left; o.left_stride = left_stride; o.right = right; o.right_stride = right_stride;
+    o.svals = svals; o.svals_stride = svals_stride; o.info = info; o.k = k; o.lc = left_canonical;
+    // pinned read-back area of this slot (a slot is only ever written from one stream at a time)
+    PinSlot& pin = g_pin[pin_slot];
+    if (pin.jobs_cap < (size_t)njobs) {
+        if (pin.host) { MPSB_CUDA(cudaDeviceSynchronize()); cudaFreeHost(pin.host); pin.host = nullptr; }
+        pin.jobs_cap = (size_t)njobs > 4096 ? (size_t)njobs : 4096;
+        MPSB_CUDA(cudaHostAlloc((void**)&pin.host, MAX_CHECKS * pin.jobs_cap * sizeof(Misc), cudaHostAllocDefault));
+    }
+    for (int i = 0; i < MAX_CHECKS; ++i)
+        if (!pin.ev[i]) MPSB_CUDA(cudaEventCreateWithFlags(&pin.ev[i], cudaEventDisableTiming));
+    r.pin = &pin;
+    static bool attrs = false;
+    if (!attrs) {
+        MPSB_CUDA(cudaFuncSetAttribute(bj_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, APPLY_SMEM));
+        MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM));
+        attrs = true;
+    }
+    // keep the input: the weighted factor is recomputed from it at the end (see large_finish)
+    MPSB_CUDA(cudaMemcpy2DAsync(r.M0, lo.m0 * sizeof(cf), X, (size_t)x_job_stride * sizeof(cf),
+                                (size_t)nv * L * sizeof(cf), njobs, cudaMemcpyDeviceToDevice, st));
+    bj_init_kernel<<<dim3(148, njobs), 256, 0, st>>>(p);
+    MPSB_LAUNCH_CHECK("bj_init_kernel");
+    return 0;
+}
+
+// one sweep onto the run's stream, followed every CHECK_EVERY sweeps by a flag read-back
+static int large_enqueue_sweep(LargeRun& r) {
+    const LargeParams& p = r.p;
+    const LargeLayout& lo = r.lo;
+    cudaStream_t st = r.st;
+    for (int rd = 0; rd < r.nrounds; ++rd) {
+        if (!(r.skip & 1)) bj_gram_evd_kernel<<<dim3(lo.npairs, r.njobs), LT, GRAM_SMEM, st>>>(p, rd, rd == 0 ? 1 : 0);
+        if (!(r.skip & 4))
+            bj_apply_kernel<<<dim3((r.ntx + r.ntz + NT_APPLY - 1) / NT_APPLY, lo.npairs, r.njobs), LT, APPLY_SMEM, st>>>(
+                p, rd, r.ntx, r.ntx + r.ntz);
+    }
+    bj_sweep_end_kernel<<<(r.njobs + 127) / 128, 128, 0, st>>>(p, r.njobs);
+    MPSB_LAUNCH_CHECK("bj_round kernels");
+    r.sweeps_queued += 1;
+    if (r.sweeps_queued % CHECK_EVERY == 0 && r.sweeps_queued >= 4) {
+        const int slot = (r.check_head + r.checks_out) % MAX_CHECKS;
+        MPSB_CUDA(cudaMemcpyAsync(r.pin->host + (size_t)slot * r.pin->jobs_cap, p.misc, sizeof(Misc) * (size_t)r.njobs,
+                                  cudaMemcpyDeviceToHost, st));
+        MPSB_CUDA(cudaEventRecord(r.pin->ev[slot], st));
+        r.checks_out += 1;
+    }
+    return 0;
+}
+
+// Advance a run as far as possible without blocking (block = true: wait for its oldest check).
+// Returns 0 or an error; sets r.done once every job has converged or the sweep limit is queued.
+static int large_advance(LargeRun& r, bool block) {
+    while (!r.done) {
+        if (r.checks_out == MAX_CHECKS || (r.checks_out > 0 && r.sweeps_queued >= r.max_outer)) {
+            cudaEvent_t ev = r.pin->ev[r.check_head];
+            if (block) MPSB_CUDA(cudaEventSynchronize(ev));
+            else {
+                cudaError_t q = cudaEventQuery(ev);
+                if (q == cudaErrorNotReady) return 0;
+                MPSB_CUDA(q);
+            }
+            const Misc* m = r.pin->host + (size_t)r.check_head * r.pin->jobs_cap;
+            bool any = false;
+            for (int j = 0; j < r.njobs; ++j) any = any || m[j].active != 0;
+            r.check_head = (r.check_head + 1) % MAX_CHECKS;
+            r.checks_out -= 1;
+            if (!any) { r.done = true; break; }
+            continue;
+        }
+        if (r.sweeps_queued >= r.max_outer) { r.done = true; break; }
+        int rc = large_enqueue_sweep(r);
+        if (rc) return rc;
+    }
+    return 0;
+}
+
+static int large_finish(LargeRun& r) {
+    LargeParams& p = r.p;
+    const LargeLayout& lo = r.lo;
+    cudaStream_t st = r.st;
+    const int njobs = r.njobs;
+    // Every block rotation is a 32-term fp32 GEMM, so after several hundred of them Z has drifted
+    // from unitarity by ~1e-5 (and X = Z M with it), which would show up 1:1 in the singular
+    // values.  Re-orthonormalise Z with one Newton-Schulz step, Z <- (3/2 I - 1/2 Z Z^H) Z, and
+    // recompute X = Z M from the saved input: the split stays an exact projection, the
+    // accumulated error is gone, and the rows of X stay orthogonal to second order.
+    int rc = launch_cgemm(p.Z, lo.nvp, 1, 0, (int64_t)lo.z, p.Z, 1, lo.nvp, 1, (int64_t)lo.z,
+                          r.Rbuf, lo.nvp, (int64_t)lo.z, lo.nvp, lo.nvp, lo.nvp, njobs, st);
+    if (rc) return rc;
+    bj_ns_kernel<<<dim3(148, njobs), 256, 0, st>>>(r.Rbuf, (int64_t)lo.z, lo.nvp);
+    rc = launch_cgemm(r.Rbuf, lo.nvp, 1, 0, (int64_t)lo.z, p.Z, lo.nvp, 1, 0, (int64_t)lo.z,
+                      r.Z2, lo.nvp, (int64_t)lo.z, lo.nvp, lo.nvp, lo.nvp, njobs, st);
+    if (rc) return rc;
+    rc = launch_cgemm(r.Z2, lo.nvp, 1, 0, (int64_t)lo.z, r.M0, r.L, 1, 0, (int64_t)lo.m0,
+                      p.X, r.L, p.x_stride, lo.nvp, r.L, r.nv, njobs, st);
+    if (rc) return rc;
+    p.Z = r.Z2;
+    bj_sigma_kernel<<<dim3((lo.nvp + LT / 32 - 1) / (LT / 32), njobs), LT, 0, st>>>(p);
+    bj_rank_kernel<<<dim3((lo.nvp + 127) / 128, njobs), 128, 0, st>>>(p);
+    bj_write_kernel<<<dim3(32, njobs), LT, 0, st>>>(p, r.o);
+    MPSB_LAUNCH_CHECK("bj_write_kernel");
+    return 0;
+}
+
 }  // namespace
 
 int svd_large_padded_rows(int nv) { return (nv + P - 1) / P * P; }
@@ -530,110 +709,42 @@ int launch_svd_large(cf* X, int64_t x_job_stride, int njobs, int nv, int L, int 
                      cudaStream_t st) {
     (void)ndesc;
     if (njobs <= 0) return 0;
-    MPSB_ARG(work != nullptr, "svd_large: workspace missing");
-    MPSB_ARG(njobs <= 65535, "svd_large: njobs %d > 65535", njobs);
-    LargeLayout lo = large_layout(nv, L);
-    MPSB_ARG(x_job_stride >= (int64_t)lo.nvp * L, "svd_large: X stride too small for the padded rows");
-    LargeParams p;
-    p.X = X; p.x_stride = x_job_stride;
-    // workspace: [njobs][Z] [njobs][G] [njobs][Q] [njobs][sigma|perm] [njobs][misc]
-    cf* w = work;
-    p.Z = w; p.z_stride = (int64_t)lo.z; w += lo.z * njobs;
-    p.rotflag = (int*)w; w += lo.g * njobs;          // (region of the former G buffer)
-    p.Q = w; w += lo.g * njobs;
-    p.g_stride = (int64_t)lo.g;
-    p.sigma = (float*)w; p.perm = (int*)((float*)w + (size_t)lo.s * njobs); p.s_stride = (int64_t)lo.s; w += lo.s * njobs;
-    p.misc = (Misc*)w; w += lo.misc * njobs;
-    cf* Rbuf = w; w += lo.z * njobs;
-    cf* Z2 = w; w += lo.z * njobs;
-    cf* M0 = w;
-    p.nv = nv; p.L = L; p.nvp = lo.nvp; p.nb = lo.nb; p.npairs = lo.npairs;
-    // the Gram entries carry rounding noise ~ eps*sqrt(L)*sqrt(G_ii G_jj): keep the threshold above it
-    float tol = 3e-6f;
-    float floor_ = 4.0f * 5.96e-8f * sqrtf((float)L);
-    if (floor_ > tol) tol = floor_;
-    p.tol2 = tol * tol;
-    float eta = ABS_ETA;
-    if (const char* e = getenv("MPSB_LARGE_ETA")) eta = (float)atof(e);          // experiments only
-    p.eta2 = eta * eta;
+    LargeRun r;
+    int rc = large_begin(r, X, x_job_stride, njobs, nv, L, k, left_canonical, descs, nbatch, left, left_stride,
+                         right, right_stride, svals, svals_stride, info, work, st, PIN_SLOTS - 1);
+    if (rc) return rc;
+    rc = large_advance(r, true);
+    if (rc) return rc;
+    return large_finish(r);
+}
 
-    // keep the input: the weighted factor is recomputed from it at the end (see below)
-    MPSB_CUDA(cudaMemcpy2DAsync(M0, lo.m0 * sizeof(cf), X, (size_t)x_job_stride * sizeof(cf),
-                                (size_t)nv * L * sizeof(cf), njobs, cudaMemcpyDeviceToDevice, st));
-    bj_init_kernel<<<dim3(148, njobs), 256, 0, st>>>(p);
-    MPSB_LAUNCH_CHECK("bj_init_kernel");
-    const int nrounds = lo.nb > 2 ? lo.nb - 1 : 1;
-    const int ntx = (L + CT - 1) / CT, ntz = (lo.nvp + CT - 1) / CT;
-    MPSB_CUDA(cudaFuncSetAttribute(bj_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, APPLY_SMEM));
-    MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM));
-    int skip = 0, max_outer = MAX_OUTER;         // timing experiments only
-    if (const char* e = getenv("MPSB_LARGE_SKIP")) skip = atoi(e);
-    if (const char* e = getenv("MPSB_LARGE_SWEEPS")) max_outer = atoi(e);
-    // The sweep loop stops as soon as every job has converged instead of launching the remaining
-    // sweeps as no-ops (2 800 empty launches per call at the typical 10 sweeps): every second sweep
-    // the per-job flags are copied to pinned host memory behind an event, and the event of the
-    // PREVIOUS check is inspected -- the stream always has two sweeps queued, the GPU never idles.
-    static Misc* pinned = nullptr;
-    static size_t pinned_jobs = 0;
-    static cudaEvent_t ev[2] = {nullptr, nullptr};
-    if (pinned_jobs < (size_t)njobs) {
-        if (pinned) cudaFreeHost(pinned);
-        pinned_jobs = (size_t)njobs > 1024 ? (size_t)njobs : 1024;
-        MPSB_CUDA(cudaHostAlloc((void**)&pinned, 2 * pinned_jobs * sizeof(Misc), cudaHostAllocDefault));
+// Several independent solves (different shapes, disjoint outputs), each on its own stream:
+// begin all, keep every stream fed by polling, finish each as soon as it has converged.
+
+int launch_svd_large_multi(const LargeMultiJob* jobs, int n) {
+    std::vector<LargeRun> runs(n);
+    std::vector<char> finished(n, 0);
+    for (int i = 0; i < n; ++i) {
+        const LargeMultiJob& j = jobs[i];
+        int rc = large_begin(runs[i], j.X, j.x_job_stride, j.njobs, j.nv, j.L, j.k, j.left_canonical, j.descs, j.nbatch,
+                             nullptr, 0, nullptr, 0, nullptr, 0, j.info, j.work, j.st, j.pin_slot);
+        if (rc) return rc;
     }
-    if (!ev[0]) {
-        MPSB_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
-        MPSB_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
-    }
-    int pending = -1, slot = 0;
-    for (int sweep = 0; sweep < max_outer; ++sweep) {
-        for (int r = 0; r < nrounds; ++r) {
-            if (!(skip & 1)) bj_gram_evd_kernel<<<dim3(lo.npairs, njobs), LT, GRAM_SMEM, st>>>(p, r, r == 0 ? 1 : 0);
-            if (!(skip & 4))
-                bj_apply_kernel<<<dim3((ntx + ntz + NT_APPLY - 1) / NT_APPLY, lo.npairs, njobs), LT, APPLY_SMEM, st>>>(p, r, ntx, ntx + ntz);
-        }
-        bj_sweep_end_kernel<<<(njobs + 127) / 128, 128, 0, st>>>(p, njobs);
-        if (sweep >= 3 && (sweep & 1) && sweep + 1 < max_outer) {
-            if (pending >= 0) {
-                MPSB_CUDA(cudaEventSynchronize(ev[pending]));
-                const Misc* m = pinned + (size_t)pending * pinned_jobs;
-                bool any = false;
-                for (int j = 0; j < njobs; ++j) any = any || m[j].active != 0;
-                if (!any) break;
+    int left = n;
+    unsigned spins = 0;
+    while (left > 0) {
+        for (int i = 0; i < n; ++i) {
+            if (finished[i]) continue;
+            int rc = large_advance(runs[i], left == 1);      // the last one may block instead of spinning
+            if (rc) return rc;
+            if (runs[i].done) {
+                rc = large_finish(runs[i]);
+                if (rc) return rc;
+                finished[i] = 1;
+                left -= 1;
             }
-            MPSB_CUDA(cudaMemcpyAsync(pinned + (size_t)slot * pinned_jobs, p.misc, sizeof(Misc) * (size_t)njobs,
-                                      cudaMemcpyDeviceToHost, st));
-            MPSB_CUDA(cudaEventRecord(ev[slot], st));
-            pending = slot;
-            slot ^= 1;
         }
+        if ((++spins & 15u) == 0) sched_yield();
     }
-    MPSB_LAUNCH_CHECK("bj_round kernels");
-    // Every block rotation is a 32-term fp32 GEMM, so after several hundred of them Z has drifted
-    // from unitarity by ~1e-5 (and X = Z M with it), which would show up 1:1 in the singular
-    // values.  Re-orthonormalise Z with one Newton-Schulz step, Z <- (3/2 I - 1/2 Z Z^H) Z, and
-    // recompute X = Z M from the saved input: the split stays an exact projection, the
-    // accumulated error is gone, and the rows of X stay orthogonal to second order.
-    {
-        int rc = launch_cgemm(p.Z, lo.nvp, 1, 0, (int64_t)lo.z, p.Z, 1, lo.nvp, 1, (int64_t)lo.z,
-                              Rbuf, lo.nvp, (int64_t)lo.z, lo.nvp, lo.nvp, lo.nvp, njobs, st);
-        if (rc) return rc;
-        bj_ns_kernel<<<dim3(148, njobs), 256, 0, st>>>(Rbuf, (int64_t)lo.z, lo.nvp);
-        rc = launch_cgemm(Rbuf, lo.nvp, 1, 0, (int64_t)lo.z, p.Z, lo.nvp, 1, 0, (int64_t)lo.z,
-                          Z2, lo.nvp, (int64_t)lo.z, lo.nvp, lo.nvp, lo.nvp, njobs, st);
-        if (rc) return rc;
-        rc = launch_cgemm(Z2, lo.nvp, 1, 0, (int64_t)lo.z, M0, L, 1, 0, (int64_t)lo.m0,
-                          p.X, L, p.x_stride, lo.nvp, L, nv, njobs, st);
-        if (rc) return rc;
-        p.Z = Z2;
-    }
-    bj_sigma_kernel<<<dim3((lo.nvp + LT / 32 - 1) / (LT / 32), njobs), LT, 0, st>>>(p);
-    bj_rank_kernel<<<dim3((lo.nvp + 127) / 128, njobs), 128, 0, st>>>(p);
-    OutParams o;
-    o.descs = descs; o.nbatch = nbatch > 0 ? nbatch : 1;
-    o.left = left; o.left_stride = left_stride; o.right = right; o.right_stride = right_stride;
-    o.svals = svals; o.svals_stride = svals_stride; o.info = info; o.k = k; o.lc = left_canonical;
-    bj_write_kernel<<<dim3(32, njobs), LT, 0, st>>>(p, o);
-    MPSB_LAUNCH_CHECK("bj_write_kernel");
     return 0;
 }
