@@ -51,6 +51,18 @@ __device__ __forceinline__ void pair_blocks(int nb, int r, int g, int& I, int& J
     else { I = (r + g) % m; J = (r - g + m) % m; }
 }
 
+// Programmatic dependent launch: the round kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so a grid is scheduled while its predecessor
+// in the stream drains and only this instruction waits for the predecessor's memory to be visible.
+// A single matrix runs ~600 dependent rounds of two ~8 us kernels: the launch latency hidden this
+// way is a fixed share of each of them.
+// launch_dependents right after the wait: the next grid becomes resident (and blocks in its own
+// wait) while this one computes, never more than one grid ahead.
+__device__ __forceinline__ void griddep_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 __device__ __forceinline__ int pair_row(int I, int J, int t) { return t < BLK ? I * BLK + t : J * BLK + (t - BLK); }
 
 __global__ void bj_init_kernel(LargeParams p) {
@@ -114,6 +126,7 @@ constexpr int GRAM_SMEM = (2 * P * XS_LD + 2 * P * (P + 1)) * (int)sizeof(cf);
 
 __global__ void __launch_bounds__(LT) bj_gram_evd_kernel(LargeParams p, int round, int first_round) {
     const int job = blockIdx.y, g = blockIdx.x;
+    griddep_wait();
     if (!p.misc[job].active) return;
     extern __shared__ float4 gram_smem[];
     cf* Xbuf = reinterpret_cast<cf*>(gram_smem);
@@ -342,12 +355,13 @@ __global__ void __launch_bounds__(LT) bj_gram_evd_kernel(LargeParams p, int roun
 // its time on the long scoreboard: FMA pipe 39 % -- profiles/r1_svd_large_ncu_full.txt).  A thread
 // owns two columns (c, c + CT/2) and 8 of the 32 output rows: per k two LDS.64 of T and four
 // broadcast LDS.128 of Q^T for 64 FFMA.
-constexpr int NT_APPLY = 4;
+constexpr int NT_APPLY = 4;                                  // at most; fewer for small batches (large_begin)
 constexpr int TS_LD = CT + 2;                                 // row stride of a staged tile (elements)
 constexpr int APPLY_SMEM = (P * (P + 2) + 2 * P * TS_LD) * (int)sizeof(cf);
 
-__global__ void __launch_bounds__(LT) bj_apply_kernel(LargeParams p, int round, int ntx, int ntot) {
+__global__ void __launch_bounds__(LT) bj_apply_kernel(LargeParams p, int round, int ntx, int ntot, int nt_cta) {
     const int job = blockIdx.z, g = blockIdx.y;
+    griddep_wait();
     if (!p.misc[job].active) return;
     if (!p.rotflag[(size_t)job * p.npairs + g]) return;      // no rotation in this pair: Q = I
     extern __shared__ float4 apply_smem[];
@@ -355,8 +369,8 @@ __global__ void __launch_bounds__(LT) bj_apply_kernel(LargeParams p, int round, 
     cf* Tbuf = reinterpret_cast<cf*>(apply_smem) + P * (P + 2);
     int I, J;
     pair_blocks(p.nb, round, g, I, J);
-    const int tile0 = blockIdx.x * NT_APPLY;
-    const int nt = min(NT_APPLY, ntot - tile0);
+    const int tile0 = blockIdx.x * nt_cta;
+    const int nt = min(nt_cta, ntot - tile0);
     cf* const Xb = p.X + (size_t)job * p.x_stride;
     cf* const Zb = p.Z + (size_t)job * p.z_stride;
     auto issue = [&](int tile, cf* buf) {
@@ -424,6 +438,7 @@ __global__ void bj_ns_kernel(cf* R, int64_t stride, int n) {
 }
 
 __global__ void bj_sweep_end_kernel(LargeParams p, int njobs) {
+    griddep_wait();
     int job = blockIdx.x * blockDim.x + threadIdx.x;
     if (job >= njobs) return;
     Misc& m = p.misc[job];
@@ -543,7 +558,7 @@ struct LargeRun {
     LargeLayout lo;
     OutParams o;
     cf *Rbuf, *Z2, *M0;
-    int njobs, nv, L, nrounds, ntx, ntz, max_outer, skip;
+    int njobs, nv, L, nrounds, ntx, ntz, max_outer, skip, nt_cta, pdl;
     cudaStream_t st;
     PinSlot* pin;
     int sweeps_queued = 0;
@@ -586,7 +601,15 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
     r.lo = lo; r.njobs = njobs; r.nv = nv; r.L = L; r.st = st;
     r.nrounds = lo.nb > 2 ? lo.nb - 1 : 1;
     r.ntx = (L + CT - 1) / CT; r.ntz = (lo.nvp + CT - 1) / CT;
-    r.skip = 0; r.max_outer = MAX_OUTER;          // timing experiments only
+    // column tiles per apply CTA: as many as keep one full wave of CTAs (3 per SM) in the launch;
+    // a small batch is latency bound and wants the shortest CTAs
+    r.nt_cta = 1;
+    for (int nt = NT_APPLY; nt > 1; nt >>= 1)
+        if ((long long)njobs * lo.npairs * ((r.ntx + r.ntz + nt - 1) / nt) >= 3 * 148) { r.nt_cta = nt; break; }
+    r.pdl = 1;
+    if (const char* e = getenv("MPSB_LARGE_NT")) r.nt_cta = atoi(e) > 0 ? atoi(e) : r.nt_cta;   // timing experiments only
+    if (const char* e = getenv("MPSB_LARGE_PDL")) r.pdl = atoi(e);
+    r.skip = 0; r.max_outer = MAX_OUTER;
     if (const char* e = getenv("MPSB_LARGE_SKIP")) r.skip = atoi(e);
     if (const char* e = getenv("MPSB_LARGE_SWEEPS")) r.max_outer = atoi(e);
     OutParams& o = r.o;
@@ -622,13 +645,24 @@ static int large_enqueue_sweep(LargeRun& r) {
     const LargeParams& p = r.p;
     const LargeLayout& lo = r.lo;
     cudaStream_t st = r.st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = r.pdl ? 1 : 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
     for (int rd = 0; rd < r.nrounds; ++rd) {
-        if (!(r.skip & 1)) bj_gram_evd_kernel<<<dim3(lo.npairs, r.njobs), LT, GRAM_SMEM, st>>>(p, rd, rd == 0 ? 1 : 0);
-        if (!(r.skip & 4))
-            bj_apply_kernel<<<dim3((r.ntx + r.ntz + NT_APPLY - 1) / NT_APPLY, lo.npairs, r.njobs), LT, APPLY_SMEM, st>>>(
-                p, rd, r.ntx, r.ntx + r.ntz);
+        if (!(r.skip & 1)) {
+            cfg.gridDim = dim3(lo.npairs, r.njobs); cfg.blockDim = dim3(LT); cfg.dynamicSmemBytes = GRAM_SMEM;
+            MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_gram_evd_kernel, p, rd, rd == 0 ? 1 : 0));
+        }
+        if (!(r.skip & 4)) {
+            cfg.gridDim = dim3((r.ntx + r.ntz + r.nt_cta - 1) / r.nt_cta, lo.npairs, r.njobs);
+            cfg.blockDim = dim3(LT); cfg.dynamicSmemBytes = APPLY_SMEM;
+            MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_apply_kernel, p, rd, r.ntx, r.ntx + r.ntz, r.nt_cta));
+        }
     }
-    bj_sweep_end_kernel<<<(r.njobs + 127) / 128, 128, 0, st>>>(p, r.njobs);
+    cfg.gridDim = dim3((r.njobs + 127) / 128); cfg.blockDim = dim3(128); cfg.dynamicSmemBytes = 0;
+    MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_sweep_end_kernel, p, r.njobs));
     MPSB_LAUNCH_CHECK("bj_round kernels");
     r.sweeps_queued += 1;
     if (r.sweeps_queued % CHECK_EVERY == 0 && r.sweeps_queued >= 4) {
