@@ -42,7 +42,9 @@ struct LargeParams {
     Misc* misc;
     int nv, L, nvp, nb, npairs;
     float tol2, eta2;
+    long long* clk;              // phase clocks of CTA (0,0) (MPSB_LARGE_CLOCKS=1, profiling only) or nullptr
 };
+#define BJ_CLK(i) do { if (p.clk && blockIdx.x == 0 && blockIdx.y == 0 && threadIdx.x == 0) p.clk[i] = clock64(); } while (0)
 
 __device__ __forceinline__ void pair_blocks(int nb, int r, int g, int& I, int& J) {
     if (nb == 2) { I = 0; J = 1; return; }
@@ -86,15 +88,25 @@ __global__ void bj_init_kernel(LargeParams p) {
 
 __device__ __forceinline__ void evd_rot_params(float a, float b, float gr, float gi, float g2,
                                                float& c, float& sr, float& si) {
+    // On the critical path of every rotation set (16-31 dependent sets per launch): four MUFU
+    // approximations instead of an IEEE division and square root.  The angle only has to be close
+    // to the annihilating one; unitarity comes from c being DERIVED from s (and from the
+    // Newton-Schulz step on Q).
     float rg = rsqrtf(g2);
     float zeta = (a - b) * (0.5f * rg);
-    float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
+    float az = fminf(fabsf(zeta), 1e18f);                    // keeps az^2 finite
+    float z2 = fmaf(az, az, 1.0f);
+    float t = copysignf(__fdividef(1.0f, az + z2 * rsqrtf(z2)), zeta);
     float ct = (t * rsqrtf(fmaf(t, t, 1.0f))) * rg;
     sr = ct * gr;
     si = ct * gi;
     float h = fmaf(sr, sr, si * si);
-    float poly = fmaf(h, fmaf(h, fmaf(h, fmaf(h, 0.02734375f, 0.0390625f), 0.0625f), 0.125f), 0.5f);
-    c = (h < 0.0625f) ? fmaf(-h, poly, 1.0f) : sqrtf(fmaf(-sr, sr, fmaf(-si, si, 1.0f)));
+    if (h < 0.0625f) {
+        float poly = fmaf(h, fmaf(h, fmaf(h, fmaf(h, 0.02734375f, 0.0390625f), 0.0625f), 0.125f), 0.5f);
+        c = fmaf(-h, poly, 1.0f);
+    } else {
+        c = sqrtf(fmaf(-sr, sr, fmaf(-si, si, 1.0f)));
+    }
 }
 
 // 8-byte cp.async (one complex64; always aligned) with zero fill when !valid
@@ -120,17 +132,36 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // (First versions: three kernels -- Gram with 2 x 2 tiles, a 256-thread EVD with a converged inner
 // iteration, later a warp-per-problem EVD kernel -- and a G round trip through L2; then this kernel
 // with a single-warp pass, which left 7 of 8 warps at a barrier: profiles/r1_svd_large_ncu_full.txt.)
+// rotation `idx` (0..15) of set t of a pass over the two 16-row blocks of a pair: in the first
+// round of a sweep the 15 intra-block sets come first (circle method inside each block, 8 pairs
+// per block), then the 16 cross sets (i, 16 + (i + s) mod 16)
+__device__ __forceinline__ void set_pair(int t, int first_round, int idx, int& pp, int& qq) {
+    if (first_round && t < BLK - 1) {
+        const int blk = idx >> 3, i = idx & 7, m = BLK - 1;
+        int a_, b_;
+        if (i == 0) { a_ = m; b_ = t; }
+        else { a_ = t + i; a_ = a_ >= m ? a_ - m : a_; b_ = t - i; b_ = b_ < 0 ? b_ + m : b_; }      // (t +- i) mod 15
+        pp = blk * BLK + min(a_, b_); qq = blk * BLK + max(a_, b_);
+    } else {
+        const int sft = first_round ? t - (BLK - 1) : t;
+        pp = idx; qq = BLK + ((idx + sft) & (BLK - 1));
+    }
+}
+
 constexpr int GK = 64;                       // columns per Gram tile
 constexpr int XS_LD = GK + 1;
-constexpr int GRAM_SMEM = (2 * P * XS_LD + 2 * P * (P + 1)) * (int)sizeof(cf);
+constexpr int GRAM_MAX_STAGES = 4;           // a small batch is bound by the latency of its tile loads: deeper ring
+constexpr int gram_smem_bytes(int nst) { return (nst * P * XS_LD + 2 * P * (P + 1)) * (int)sizeof(cf); }
 
-__global__ void __launch_bounds__(LT) bj_gram_evd_kernel(LargeParams p, int round, int first_round) {
+template <int NTHR>                          // 256, or 512 for launches with fewer CTAs than SMs (halves Gram and NS)
+__global__ void __launch_bounds__(NTHR) bj_gram_evd_kernel(LargeParams p, int round, int first_round, int nst) {
+    constexpr int NGRP = NTHR / 64, NWARP = NTHR / 32;
     const int job = blockIdx.y, g = blockIdx.x;
     griddep_wait();
     if (!p.misc[job].active) return;
     extern __shared__ float4 gram_smem[];
     cf* Xbuf = reinterpret_cast<cf*>(gram_smem);
-    cf (*Gs)[P + 1] = reinterpret_cast<cf (*)[P + 1]>(Xbuf + 2 * P * XS_LD);
+    cf (*Gs)[P + 1] = reinterpret_cast<cf (*)[P + 1]>(Xbuf + nst * P * XS_LD);
     cf (*Qs)[P + 1] = Gs + P;
     int I, J;
     pair_blocks(p.nb, round, g, I, J);
@@ -139,7 +170,7 @@ __global__ void __launch_bounds__(LT) bj_gram_evd_kernel(LargeParams p, int roun
     const int tx = t64 & 7, ty = t64 >> 3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto issue = [&](int c0, cf* buf) {
-        for (int e = threadIdx.x; e < P * GK; e += LT) {
+        for (int e = threadIdx.x; e < P * GK; e += NTHR) {
             const int r = e / GK, c = e % GK;
             const bool valid = c0 + c < p.L;
             cp_async8(&buf[r * XS_LD + c], valid ? X + (size_t)pair_row(I, J, r) * p.L + c0 + c : X, valid);
@@ -152,15 +183,20 @@ __global__ void __launch_bounds__(LT) bj_gram_evd_kernel(LargeParams p, int roun
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = cf_make(0.f, 0.f);
     const int ntile = (p.L + GK - 1) / GK;
-    issue(0, Xbuf);
+    BJ_CLK(0);
+    for (int t = 0; t < nst - 1 && t < ntile; ++t) issue(t * GK, Xbuf + t * (P * XS_LD));
     for (int t = 0; t < ntile; ++t) {
-        const cf* Xs = Xbuf + (t & 1) * (P * XS_LD);
-        if (t + 1 < ntile) { issue((t + 1) * GK, Xbuf + ((t + 1) & 1) * (P * XS_LD)); cp_async_wait<1>(); }
+        const cf* Xs = Xbuf + (t % nst) * (P * XS_LD);
+        if (t + nst - 1 < ntile) issue((t + nst - 1) * GK, Xbuf + ((t + nst - 1) % nst) * (P * XS_LD));
+        const int pending = min(ntile - 1 - t, nst - 1);     // groups that may still be in flight
+        if (pending >= 3) cp_async_wait<3>();
+        else if (pending == 2) cp_async_wait<2>();
+        else if (pending == 1) cp_async_wait<1>();
         else cp_async_wait<0>();
         __syncthreads();
 #pragma unroll 4
-        for (int cc = 0; cc < GK / 4; ++cc) {
-            const int c = grp * (GK / 4) + cc;
+        for (int cc = 0; cc < GK / NGRP; ++cc) {
+            const int c = grp * (GK / NGRP) + cc;
             cf a[4], b[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) a[i] = Xs[(ty + 8 * i) * XS_LD + c];
@@ -173,7 +209,8 @@ __global__ void __launch_bounds__(LT) bj_gram_evd_kernel(LargeParams p, int roun
         }
         __syncthreads();
     }
-    for (int q = 0; q < 4; ++q) {
+    BJ_CLK(1);
+    for (int q = 0; q < NGRP; ++q) {
         if (grp == q) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -195,8 +232,8 @@ __global__ void __launch_bounds__(LT) bj_gram_evd_kernel(LargeParams p, int roun
     const float sc = mx > 0.f ? ldexpf(1.0f, 1 - ex) : 1.0f;
     __syncthreads();
 #pragma unroll
-    for (int ii = 0; ii < 4; ++ii) {
-        const int i = warp + 8 * ii;
+    for (int ii = 0; ii < P / NWARP; ++ii) {
+        const int i = warp + NWARP * ii;
         cf v = Gs[i][lane];
         Gs[i][lane] = cf_make(v.x * sc, v.y * sc);
         Qs[i][lane] = cf_make(i == lane ? 1.f : 0.f, 0.f);
@@ -214,88 +251,96 @@ __global__ void __launch_bounds__(LT) bj_gram_evd_kernel(LargeParams p, int roun
     // ~10 sweeps for flat spectra, ~20 for graded ones (tests/_jacobi_model.py notes).
     const float gmax_s = p.misc[job].gmax * sc;
     const float eta2g = p.eta2 * gmax_s;
+    BJ_CLK(2);
     // ONE pass over the pairs of the two 16-row blocks, each rotation computed from the current
     // (two-sidedly updated) Gram entries: the 16 cross sets (i, 16 + (i+s) mod 16), preceded in the
     // first round of an outer sweep by the 15 intra-block sets (circle method inside each block).
     // This is the scalar cyclic Jacobi sweep of svd_small.cu carried out on the Gram matrix: the
     // outer iteration needs the same ~9 sweeps, but a pair step costs 16 (31) rotation sets instead
     // of the 5 x 31 of a fully converged inner eigen-decomposition.
+    // A set is 16 disjoint rotations J_i on rows/columns (p_i, q_i): G <- J G J^H splits into 16 x 16
+    // independent 2 x 2 blocks  B_ij = G[{p_i,q_i}][{p_j,q_j}] <- J_i B_ij J_j^H, one per thread
+    // (thread = (i, j)); Q <- J Q likewise (thread (i, j): rows p_i, q_i, columns 2j, 2j+1).  The
+    // sixteen lanes of warp 0 derive the rotations; the (p, q) of every set come from a table built
+    // once per launch.  Two barriers per set.  (First version: rows then columns, 2 rotations per warp, 3 barriers per set and
+    // ~1 400 cycles per set on the critical path -- half of this kernel for a single matrix.)
+    float4* prm = reinterpret_cast<float4*>(Xbuf);           // [16] (c, s.re, s.im, rotate?), tile ring is free now
+    unsigned short* pairtab = reinterpret_cast<unsigned short*>(prm + 16);      // [nsets][16]  p | q << 8
     int total_rot = 0;
     const int nsets = (first_round ? (BLK - 1) : 0) + BLK;
+    for (int e = threadIdx.x; e < nsets * 16; e += NTHR) {
+        int pp, qq;
+        set_pair(e >> 4, first_round, e & 15, pp, qq);
+        pairtab[e] = (unsigned short)(pp | (qq << 8));
+    }
+    __syncthreads();
+    const int ri = (threadIdx.x >> 4) & 15, rj = threadIdx.x & 15;
     for (int t = 0; t < nsets; ++t) {
-        bool dorot = false;
-        float c = 1.f, sr = 0.f, si = 0.f;
-        int pq = 0;
-        if (lane < P / 2) {
-            int pp, qq;
-            if (first_round && t < BLK - 1) {
-                const int blk = lane >> 3, i = lane & 7, m = BLK - 1;
-                int a_, b_;
-                if (i == 0) { a_ = m; b_ = t; } else { a_ = (t + i) % m; b_ = (t - i + m) % m; }
-                pp = blk * BLK + min(a_, b_); qq = blk * BLK + max(a_, b_);
-            } else {
-                const int sft = first_round ? t - (BLK - 1) : t;
-                pp = lane; qq = BLK + ((lane + sft) & (BLK - 1));
-            }
-            const float a = Gs[pp][pp].x, b = Gs[qq][qq].x;
-            const cf gg = Gs[pp][qq];
+        const int pqi = pairtab[t * 16 + ri], pqj = pairtab[t * 16 + rj];
+        const int pi_ = pqi & 0xff, qi_ = pqi >> 8, pj_ = pqj & 0xff, qj_ = pqj >> 8;
+        int dorot = 0;
+        if (threadIdx.x < 16) {                  // rotation rj of the set (lanes 0-15 of warp 0)
+            const float a = Gs[pj_][pj_].x, b = Gs[qj_][qj_].x;
+            const cf gg = Gs[pj_][qj_];
             const float g2 = cf_abs2(gg);
-            dorot = g2 > p.tol2 * a * b && g2 > eta2g * fmaxf(a, b) && g2 > 1e-30f;
+            float c = 1.f, sr = 0.f, si = 0.f;
+            dorot = (g2 > p.tol2 * a * b && g2 > eta2g * fmaxf(a, b) && g2 > 1e-30f) ? 1 : 0;
             if (dorot) evd_rot_params(a, b, gg.x, gg.y, g2, c, sr, si);
-            pq = pp | (qq << 8);
+            prm[rj] = make_float4(c, sr, si, dorot ? 1.f : 0.f);
         }
-        const unsigned bal = __ballot_sync(0xffffffffu, dorot);
-        if (bal == 0u) continue;                 // identical in every warp: nothing to rotate in this set
-        total_rot += __popc(bal);
-        __syncthreads();                         // all warps have read G for their parameters
-        // this warp's two rotations of the set
-        float rc[2], rsr[2], rsi[2];
-        int rpq[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const int src = 2 * warp + u;
-            rc[u] = __shfl_sync(0xffffffffu, c, src);
-            rsr[u] = __shfl_sync(0xffffffffu, sr, src);
-            rsi[u] = __shfl_sync(0xffffffffu, si, src);
-            rpq[u] = __shfl_sync(0xffffffffu, pq, src);
+        const int nrot = __syncthreads_count(dorot);
+        if (nrot == 0) continue;                 // block-uniform: nothing to rotate in this set
+        total_rot += nrot;
+        const float4 Ji = prm[ri], Jj = prm[rj];
+        if (threadIdx.x < 256 && (Ji.w != 0.f || Jj.w != 0.f)) {
+            cf g00 = Gs[pi_][pj_], g01 = Gs[pi_][qj_], g10 = Gs[qi_][pj_], g11 = Gs[qi_][qj_];
+            // left: [x; y] <- J_i [x; y]:  x' = c x + s y,  y' = c y - conj(s) x
+            {
+                const float c = Ji.x, sr = Ji.y, si = Ji.z;
+                cf n00, n01, n10, n11;
+                n00.x = fmaf(c, g00.x, fmaf(sr, g10.x, -(si * g10.y)));
+                n00.y = fmaf(c, g00.y, fmaf(sr, g10.y, si * g10.x));
+                n10.x = fmaf(c, g10.x, -fmaf(sr, g00.x, si * g00.y));
+                n10.y = fmaf(c, g10.y, fmaf(si, g00.x, -(sr * g00.y)));
+                n01.x = fmaf(c, g01.x, fmaf(sr, g11.x, -(si * g11.y)));
+                n01.y = fmaf(c, g01.y, fmaf(sr, g11.y, si * g11.x));
+                n11.x = fmaf(c, g11.x, -fmaf(sr, g01.x, si * g01.y));
+                n11.y = fmaf(c, g11.y, fmaf(si, g01.x, -(sr * g01.y)));
+                g00 = n00; g01 = n01; g10 = n10; g11 = n11;
+            }
+            // right: [x, y] <- [x, y] J_j^H:  x' = c x + conj(s) y,  y' = c y - s x
+            {
+                const float c = Jj.x, sr = Jj.y, si = Jj.z;
+                cf n00, n01, n10, n11;
+                n00.x = fmaf(c, g00.x, fmaf(sr, g01.x, si * g01.y));
+                n00.y = fmaf(c, g00.y, fmaf(sr, g01.y, -(si * g01.x)));
+                n01.x = fmaf(c, g01.x, -fmaf(sr, g00.x, -(si * g00.y)));
+                n01.y = fmaf(c, g01.y, -fmaf(sr, g00.y, si * g00.x));
+                n10.x = fmaf(c, g10.x, fmaf(sr, g11.x, si * g11.y));
+                n10.y = fmaf(c, g10.y, fmaf(sr, g11.y, -(si * g11.x)));
+                n11.x = fmaf(c, g11.x, -fmaf(sr, g10.x, -(si * g10.y)));
+                n11.y = fmaf(c, g11.y, -fmaf(sr, g10.y, si * g10.x));
+                g00 = n00; g01 = n01; g10 = n10; g11 = n11;
+            }
+            Gs[pi_][pj_] = g00; Gs[pi_][qj_] = g01; Gs[qi_][pj_] = g10; Gs[qi_][qj_] = g11;
         }
-        // rows: [g_p; g_q] <- J [g_p; g_q], same for Q      (lane = column)
+        if (threadIdx.x < 256 && Ji.w != 0.f) {
+            const float c = Ji.x, sr = Ji.y, si = Ji.z;
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (!((bal >> (2 * warp + u)) & 1u)) continue;
-            const int ip = rpq[u] & 0xff, iq = rpq[u] >> 8;
-            const float pc = rc[u], ps = rsr[u], pi = rsi[u];
-            cf x = Gs[ip][lane], y = Gs[iq][lane];
-            cf nx, ny;
-            nx.x = fmaf(pc, x.x, fmaf(ps, y.x, -(pi * y.y)));
-            nx.y = fmaf(pc, x.y, fmaf(ps, y.y, pi * y.x));
-            ny.x = fmaf(pc, y.x, -fmaf(ps, x.x, pi * x.y));
-            ny.y = fmaf(pc, y.y, fmaf(pi, x.x, -(ps * x.y)));
-            Gs[ip][lane] = nx; Gs[iq][lane] = ny;
-            x = Qs[ip][lane]; y = Qs[iq][lane];
-            nx.x = fmaf(pc, x.x, fmaf(ps, y.x, -(pi * y.y)));
-            nx.y = fmaf(pc, x.y, fmaf(ps, y.y, pi * y.x));
-            ny.x = fmaf(pc, y.x, -fmaf(ps, x.x, pi * x.y));
-            ny.y = fmaf(pc, y.y, fmaf(pi, x.x, -(ps * x.y)));
-            Qs[ip][lane] = nx; Qs[iq][lane] = ny;
-        }
-        __syncthreads();
-        // columns: [g_.p, g_.q] <- [g_.p, g_.q] J^H :  p' = c p + conj(s) q ; q' = -s p + c q   (lane = row)
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            if (!((bal >> (2 * warp + u)) & 1u)) continue;
-            const int ip = rpq[u] & 0xff, iq = rpq[u] >> 8;
-            const float pc = rc[u], ps = rsr[u], pi = rsi[u];
-            const cf x = Gs[lane][ip], y = Gs[lane][iq];
-            cf nx, ny;
-            nx.x = fmaf(pc, x.x, fmaf(ps, y.x, pi * y.y));
-            nx.y = fmaf(pc, x.y, fmaf(ps, y.y, -(pi * y.x)));
-            ny.x = fmaf(pc, y.x, -fmaf(ps, x.x, -(pi * x.y)));
-            ny.y = fmaf(pc, y.y, -fmaf(ps, x.y, pi * x.x));
-            Gs[lane][ip] = nx; Gs[lane][iq] = ny;
+            for (int u = 0; u < 2; ++u) {
+                const int col = 2 * rj + u;
+                const cf x = Qs[pi_][col], y = Qs[qi_][col];
+                cf nx, ny;
+                nx.x = fmaf(c, x.x, fmaf(sr, y.x, -(si * y.y)));
+                nx.y = fmaf(c, x.y, fmaf(sr, y.y, si * y.x));
+                ny.x = fmaf(c, y.x, -fmaf(sr, x.x, si * x.y));
+                ny.y = fmaf(c, y.y, fmaf(si, x.x, -(sr * x.y)));
+                Qs[pi_][col] = nx; Qs[qi_][col] = ny;
+            }
         }
         __syncthreads();
     }
+    BJ_CLK(3);
     if (warp == 0) {
         float lam = Gs[lane][lane].x;
 #pragma unroll
@@ -316,37 +361,40 @@ __global__ void __launch_bounds__(LT) bj_gram_evd_kernel(LargeParams p, int roun
     // value) over the ~400 block rotations of a solve; after the step Q is unitary to ~1e-7.
     // R = Q Q^H into Gs, then Qo = 1.5 Q - 0.5 R Q   (thread = column `lane` of rows warp + 8 ii).
     {
-        cf r[4];
+        constexpr int RW = P / NWARP;
+        cf r[RW];
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii) r[ii] = cf_make(0.f, 0.f);
+        for (int ii = 0; ii < RW; ++ii) r[ii] = cf_make(0.f, 0.f);
 #pragma unroll 8
         for (int k = 0; k < P; ++k) {
             const cf qj = Qs[lane][k];
 #pragma unroll
-            for (int ii = 0; ii < 4; ++ii) r[ii] = cf_fma_conja(qj, Qs[warp + 8 * ii][k], r[ii]);   // Q_ik conj(Q_jk)
+            for (int ii = 0; ii < RW; ++ii) r[ii] = cf_fma_conja(qj, Qs[warp + NWARP * ii][k], r[ii]);   // Q_ik conj(Q_jk)
         }
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii) Gs[warp + 8 * ii][lane] = r[ii];
+        for (int ii = 0; ii < RW; ++ii) Gs[warp + NWARP * ii][lane] = r[ii];
     }
     __syncthreads();
     {
         cf* Qo = p.Q + (size_t)job * p.g_stride + (size_t)g * P * P;
-        cf t[4];
+        constexpr int RW = P / NWARP;
+        cf t[RW];
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii) t[ii] = cf_make(0.f, 0.f);
+        for (int ii = 0; ii < RW; ++ii) t[ii] = cf_make(0.f, 0.f);
 #pragma unroll 8
         for (int k = 0; k < P; ++k) {
             const cf qk = Qs[k][lane];
 #pragma unroll
-            for (int ii = 0; ii < 4; ++ii) t[ii] = cf_fma(Gs[warp + 8 * ii][k], qk, t[ii]);
+            for (int ii = 0; ii < RW; ++ii) t[ii] = cf_fma(Gs[warp + NWARP * ii][k], qk, t[ii]);
         }
 #pragma unroll
-        for (int ii = 0; ii < 4; ++ii) {
-            const int i = warp + 8 * ii;
+        for (int ii = 0; ii < RW; ++ii) {
+            const int i = warp + NWARP * ii;
             const cf q = Qs[i][lane];
             Qo[i * P + lane] = cf_make(1.5f * q.x - 0.5f * t[ii].x, 1.5f * q.y - 0.5f * t[ii].y);
         }
     }
+    BJ_CLK(4);
 }
 
 // rows of the pair, columns of [X | Z]:  T <- Q T   (in place).  A CTA walks NT_APPLY column
@@ -558,7 +606,7 @@ struct LargeRun {
     LargeLayout lo;
     OutParams o;
     cf *Rbuf, *Z2, *M0;
-    int njobs, nv, L, nrounds, ntx, ntz, max_outer, skip, nt_cta, pdl;
+    int njobs, nv, L, nrounds, ntx, ntz, max_outer, skip, nt_cta, pdl, gram_stages, gram_threads;
     cudaStream_t st;
     PinSlot* pin;
     int sweeps_queued = 0;
@@ -598,6 +646,11 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
     float eta = ABS_ETA;
     if (const char* e = getenv("MPSB_LARGE_ETA")) eta = (float)atof(e);          // experiments only
     p.eta2 = eta * eta;
+    p.clk = nullptr;
+    if (getenv("MPSB_LARGE_CLOCKS")) {                        // profiling only: leaks 64 bytes per call
+        MPSB_CUDA(cudaMalloc((void**)&p.clk, 8 * sizeof(long long)));
+        MPSB_CUDA(cudaMemset(p.clk, 0, 8 * sizeof(long long)));
+    }
     r.lo = lo; r.njobs = njobs; r.nv = nv; r.L = L; r.st = st;
     r.nrounds = lo.nb > 2 ? lo.nb - 1 : 1;
     r.ntx = (L + CT - 1) / CT; r.ntz = (lo.nvp + CT - 1) / CT;
@@ -606,6 +659,15 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
     r.nt_cta = 1;
     for (int nt = NT_APPLY; nt > 1; nt >>= 1)
         if ((long long)njobs * lo.npairs * ((r.ntx + r.ntz + nt - 1) / nt) >= 3 * 148) { r.nt_cta = nt; break; }
+    // Gram tile ring: two stages when several CTAs share an SM (they hide each other's loads), four
+    // when the launch has fewer CTAs than SMs
+    r.gram_stages = (long long)njobs * lo.npairs >= 2 * 148 ? 2 : GRAM_MAX_STAGES;     // (no measurable effect either way)
+    if (const char* e = getenv("MPSB_LARGE_STAGES")) r.gram_stages = atoi(e) >= 2 && atoi(e) <= GRAM_MAX_STAGES ? atoi(e) : r.gram_stages;
+    // 512 threads do not help a launch with fewer CTAs than SMs either (measured: a single 256 x 256
+    // solve 9.4 ms against 8.9 ms): one pair's Gram is bound by the FFMA issue rate of ONE SM, and the
+    // pass by its ~1 200-cycle dependent chain per rotation set (parameters 500, update 600)
+    r.gram_threads = 256;
+    if (const char* e = getenv("MPSB_LARGE_GTHREADS")) r.gram_threads = atoi(e) == 512 ? 512 : 256;   // experiments only
     r.pdl = 1;
     if (const char* e = getenv("MPSB_LARGE_NT")) r.nt_cta = atoi(e) > 0 ? atoi(e) : r.nt_cta;   // timing experiments only
     if (const char* e = getenv("MPSB_LARGE_PDL")) r.pdl = atoi(e);
@@ -629,7 +691,8 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
     static bool attrs = false;
     if (!attrs) {
         MPSB_CUDA(cudaFuncSetAttribute(bj_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, APPLY_SMEM));
-        MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GRAM_SMEM));
+        MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes(GRAM_MAX_STAGES)));
+        MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes(GRAM_MAX_STAGES)));
         attrs = true;
     }
     // keep the input: the weighted factor is recomputed from it at the end (see large_finish)
@@ -652,8 +715,14 @@ static int large_enqueue_sweep(LargeRun& r) {
     cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
     for (int rd = 0; rd < r.nrounds; ++rd) {
         if (!(r.skip & 1)) {
-            cfg.gridDim = dim3(lo.npairs, r.njobs); cfg.blockDim = dim3(LT); cfg.dynamicSmemBytes = GRAM_SMEM;
-            MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_gram_evd_kernel, p, rd, rd == 0 ? 1 : 0));
+            cfg.gridDim = dim3(lo.npairs, r.njobs); cfg.dynamicSmemBytes = gram_smem_bytes(r.gram_stages);
+            if (r.gram_threads == 512) {
+                cfg.blockDim = dim3(512);
+                MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_gram_evd_kernel<512>, p, rd, rd == 0 ? 1 : 0, r.gram_stages));
+            } else {
+                cfg.blockDim = dim3(256);
+                MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_gram_evd_kernel<256>, p, rd, rd == 0 ? 1 : 0, r.gram_stages));
+            }
         }
         if (!(r.skip & 4)) {
             cfg.gridDim = dim3((r.ntx + r.ntz + r.nt_cta - 1) / r.nt_cta, lo.npairs, r.njobs);
@@ -727,6 +796,12 @@ static int large_finish(LargeRun& r) {
     bj_rank_kernel<<<dim3((lo.nvp + 127) / 128, njobs), 128, 0, st>>>(p);
     bj_write_kernel<<<dim3(32, njobs), LT, 0, st>>>(p, r.o);
     MPSB_LAUNCH_CHECK("bj_write_kernel");
+    if (p.clk) {
+        long long h[8];
+        MPSB_CUDA(cudaMemcpy(h, p.clk, sizeof(h), cudaMemcpyDeviceToHost));
+        fprintf(stderr, "bj_gram_evd phases (cycles, CTA 0 of the last launch): gram %lld  reduce+scale %lld  pass %lld  flags+NS %lld\n",
+                h[1] - h[0], h[2] - h[1], h[3] - h[2], h[4] - h[3]);
+    }
     return 0;
 }
 
