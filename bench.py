@@ -378,6 +378,28 @@ def time_theta_tc(torch, tf32_peak):
     return out
 
 
+def cpu_dominant_shape(chi, reps):
+    """The reference's CPU arithmetic for ONE adjacent application of shape (chi, chi, chi, k = chi):
+    the complex128 numpy/LAPACK oracle (mpsim/core.py:1060-1152 restated) on random sites, all host
+    cores available to BLAS.  Reported next to the GPU number of the same shape; bounded sample."""
+    from oracle.mps_oracle import OracleMPS
+    rng = np.random.default_rng(chi)
+
+    def rnd(*shape):
+        return (rng.standard_normal(shape) + 1j * rng.standard_normal(shape)) / np.sqrt(2 * chi)
+    ora = OracleMPS(4, dtype=np.complex128)
+    ora.sites = [rnd(1, 2, chi), rnd(chi, 2, chi), rnd(chi, 2, chi), rnd(chi, 2, 1)]
+    gates = haar_gates(reps, rng).astype(np.complex128)
+    t0 = time.perf_counter()
+    for r in range(reps):
+        ora.apply_two_qudit_gate(gates[r].reshape(2, 2, 2, 2), 1, 2, maxsvals=chi)
+    dt = (time.perf_counter() - t0) / reps
+    return {"ms_per_application": dt * 1e3, "applications_per_sec": 1.0 / dt, "kind": "port",
+            "cores": len(os.sched_getaffinity(0)),
+            "sample": f"{reps} application(s) of shape ({chi},{chi},{chi}), k={chi}, random sites, complex128 numpy/LAPACK "
+                      "oracle with the host's BLAS threads"}
+
+
 def time_chi256(torch):
     """BASELINE.json configs[2]: 100-qubit brickwork, depth 20, chi = 256, one chain (replicas only)."""
     import mpsim_b200 as mp
@@ -588,10 +610,14 @@ def run_our_arm(args):
             del batch
             torch.cuda.empty_cache()
             secondary["chi256"] = time_chi256(torch)
+            if not args.no_cpu_baseline:
+                secondary["chi256"]["cpu_baseline"] = cpu_dominant_shape(256, 6)
             tf32_peak = measure_tf32_peak(torch)
             secondary["theta_tensor_core"] = time_theta_tc(torch, tf32_peak)
             secondary["tf32_tflops_measured_here"] = tf32_peak
             secondary["chi1024"] = time_chi1024(torch)
+            if not args.no_cpu_baseline:
+                secondary["chi1024"]["cpu_baseline"] = cpu_dominant_shape(1024, 1)
             t = secondary["theta_tensor_core"]["chi1024"]
             roof_theta = {"kernel": "tc_cgemm_kernel + operand split (theta, chi=1024, 8 bonds)", "bound": "tensor",
                           "achieved": t["tflops_complex_equivalent"], "peak": t["complex_tensor_core_peak_tflops"],
