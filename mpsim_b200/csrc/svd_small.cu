@@ -61,17 +61,24 @@ struct SvdSmallParams {
 // WITHOUT bias -- see tests/_jacobi_model.py:rotation_params.
 __device__ __forceinline__ void rot_params(float a, float b, float gr, float gi, float g2,
                                            float& c, float& sr, float& si, float& tg) {
+    // The tangent only steers convergence, so it is built from MUFU approximations (rsqrt, rcp:
+    // ~2 ulp) instead of an IEEE division and square root -- every lane runs this code once per
+    // four rotations.  Unitarity does not depend on it: c is derived from the s actually used.
     float rg = rsqrtf(g2);
     float zeta = (a - b) * (0.5f * rg);
-    float t = copysignf(1.0f, zeta) / (fabsf(zeta) + sqrtf(fmaf(zeta, zeta, 1.0f)));
+    float az = fminf(fabsf(zeta), 1e18f);                    // keeps az^2 finite
+    float z2 = fmaf(az, az, 1.0f);
+    float t = copysignf(__fdividef(1.0f, az + z2 * rsqrtf(z2)), zeta);
     float ct = (t * rsqrtf(fmaf(t, t, 1.0f))) * rg;
     sr = ct * gr;
     si = ct * gi;
     float h = fmaf(sr, sr, si * si);
-    float poly = fmaf(h, fmaf(h, fmaf(h, fmaf(h, 0.02734375f, 0.0390625f), 0.0625f), 0.125f), 0.5f);
-    float c_series = fmaf(-h, poly, 1.0f);
-    float c_sqrt = sqrtf(fmaf(-sr, sr, fmaf(-si, si, 1.0f)));
-    c = (h < 0.0625f) ? c_series : c_sqrt;
+    if (h < 0.0625f) {
+        float poly = fmaf(h, fmaf(h, fmaf(h, fmaf(h, 0.02734375f, 0.0390625f), 0.0625f), 0.125f), 0.5f);
+        c = fmaf(-h, poly, 1.0f);
+    } else {
+        c = sqrtf(fmaf(-sr, sr, fmaf(-si, si, 1.0f)));       // large rotations (first sweeps only)
+    }
     tg = t * (g2 * rg);
 }
 
