@@ -38,6 +38,9 @@ struct LargeParams {
     cf* Z; int64_t z_stride;     // [nvp][nvp]
     cf* Q; int64_t g_stride;     // [npairs][P][P] per job
     int* rotflag;                // [njobs][npairs]: did this round's pass rotate anything in the pair?
+    int* gcount;                 // [njobs][npairs]: arrival counter of the split Gram (zero between launches)
+    cf* gpart;                   // [njobs][npairs][nsplit][P*P] partial Gram matrices (nsplit > 1 only)
+    int nsplit;                  // CTAs sharing one pair's Gram (column ranges)
     float* sigma; int* perm; int64_t s_stride;   // [nvp]
     Misc* misc;
     int nv, L, nvp, nb, npairs;
@@ -84,6 +87,8 @@ __global__ void bj_init_kernel(LargeParams p) {
         Misc& m = p.misc[job];
         m.active = 1; m.rot = 0; m.sweeps = 0; m.gmax_next = 0u; m.gmax = 0.f;
     }
+    if (blockIdx.x == 0)
+        for (int g = threadIdx.x; g < p.npairs; g += blockDim.x) p.gcount[(size_t)job * p.npairs + g] = 0;
 }
 
 __device__ __forceinline__ void evd_rot_params(float a, float b, float gr, float gi, float g2,
@@ -182,12 +187,15 @@ __global__ void __launch_bounds__(NTHR) bj_gram_evd_kernel(LargeParams p, int ro
     for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j] = cf_make(0.f, 0.f);
-    const int ntile = (p.L + GK - 1) / GK;
+    // this CTA's column tiles: all of them, or one of nsplit contiguous ranges (blockIdx.z)
+    const int ntile_all = (p.L + GK - 1) / GK;
+    const int tile_lo = (int)(((long long)ntile_all * blockIdx.z) / p.nsplit);
+    const int ntile = (int)(((long long)ntile_all * (blockIdx.z + 1)) / p.nsplit) - tile_lo;
     BJ_CLK(0);
-    for (int t = 0; t < nst - 1 && t < ntile; ++t) issue(t * GK, Xbuf + t * (P * XS_LD));
+    for (int t = 0; t < nst - 1 && t < ntile; ++t) issue((tile_lo + t) * GK, Xbuf + t * (P * XS_LD));
     for (int t = 0; t < ntile; ++t) {
         const cf* Xs = Xbuf + (t % nst) * (P * XS_LD);
-        if (t + nst - 1 < ntile) issue((t + nst - 1) * GK, Xbuf + ((t + nst - 1) % nst) * (P * XS_LD));
+        if (t + nst - 1 < ntile) issue((tile_lo + t + nst - 1) * GK, Xbuf + ((t + nst - 1) % nst) * (P * XS_LD));
         const int pending = min(ntile - 1 - t, nst - 1);     // groups that may still be in flight
         if (pending >= 3) cp_async_wait<3>();
         else if (pending == 2) cp_async_wait<2>();
@@ -219,6 +227,33 @@ __global__ void __launch_bounds__(NTHR) bj_gram_evd_kernel(LargeParams p, int ro
                     cf& d = Gs[ty + 8 * i][tx + 8 * j];
                     d = q == 0 ? acc[i][j] : cf_add(d, acc[i][j]);
                 }
+        }
+        __syncthreads();
+    }
+    if (p.nsplit > 1) {
+        // A launch with fewer pairs than SMs (one or two matrices) spreads each pair's Gram over
+        // nsplit CTAs: partial sums go to global memory, the CTA that arrives last adds them in a
+        // fixed order and carries on alone (one pair's 32 x 32 x L Gram is otherwise bound by the
+        // FFMA issue rate of a single SM: 17 k of the 45 k cycles of this kernel at L = 256).
+        const size_t pr = (size_t)job * p.npairs + g;
+        cf* mine = p.gpart + (pr * p.nsplit + blockIdx.z) * (P * P);
+        for (int e = threadIdx.x; e < P * P; e += NTHR) mine[e] = Gs[e / P][e % P];
+        __threadfence();
+        __syncthreads();
+        __shared__ int s_last;
+        if (threadIdx.x == 0) {
+            const int ticket = atomicAdd(&p.gcount[pr], 1);
+            s_last = ticket == p.nsplit - 1;
+            if (s_last) p.gcount[pr] = 0;                    // ready for the next launch
+        }
+        __syncthreads();
+        if (!s_last) return;
+        __threadfence();
+        const cf* all = p.gpart + pr * p.nsplit * (P * P);
+        for (int e = threadIdx.x; e < P * P; e += NTHR) {
+            cf sum = __ldcg(&all[e]);
+            for (int z = 1; z < p.nsplit; ++z) sum = cf_add(sum, __ldcg(&all[(size_t)z * (P * P) + e]));
+            Gs[e / P][e % P] = sum;
         }
         __syncthreads();
     }
@@ -629,12 +664,24 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
     // workspace: [njobs][Z] [njobs][flags] [njobs][Q] [njobs][sigma|perm] [njobs][misc] R Z2 M0
     cf* w = work;
     p.Z = w; p.z_stride = (int64_t)lo.z; w += lo.z * njobs;
-    p.rotflag = (int*)w; w += lo.g * njobs;          // (region of the former G buffer)
+    p.rotflag = (int*)w; p.gcount = p.rotflag + (size_t)njobs * lo.npairs; w += lo.g * njobs;   // (region of the former G buffer)
     p.Q = w; w += lo.g * njobs;
     p.g_stride = (int64_t)lo.g;
     p.sigma = (float*)w; p.perm = (int*)((float*)w + (size_t)lo.s * njobs); p.s_stride = (int64_t)lo.s; w += lo.s * njobs;
     p.misc = (Misc*)w; w += lo.misc * njobs;
     r.Rbuf = w; w += lo.z * njobs;
+    // split Gram for launches with fewer pair-CTAs than SMs; the partial sums borrow R (used only at the end)
+    p.gpart = r.Rbuf;
+    p.nsplit = 1;
+    {
+        const int ntile_all = (L + GK - 1) / GK;
+        for (int ns = 4; ns > 1; ns >>= 1)
+            if (ns <= ntile_all && (long long)njobs * lo.npairs * ns <= 148 && (size_t)lo.npairs * ns * P * P <= lo.z) { p.nsplit = ns; break; }
+        if (const char* e = getenv("MPSB_LARGE_NSPLIT")) {   // timing experiments only
+            int ns = atoi(e);
+            if (ns >= 1 && ns <= ntile_all && (size_t)lo.npairs * ns * P * P <= lo.z) p.nsplit = ns;
+        }
+    }
     r.Z2 = w; w += lo.z * njobs;
     r.M0 = w;
     p.nv = nv; p.L = L; p.nvp = lo.nvp; p.nb = lo.nb; p.npairs = lo.npairs;
@@ -715,7 +762,7 @@ static int large_enqueue_sweep(LargeRun& r) {
     cfg.stream = st; cfg.attrs = attr; cfg.numAttrs = 1;
     for (int rd = 0; rd < r.nrounds; ++rd) {
         if (!(r.skip & 1)) {
-            cfg.gridDim = dim3(lo.npairs, r.njobs); cfg.dynamicSmemBytes = gram_smem_bytes(r.gram_stages);
+            cfg.gridDim = dim3(lo.npairs, r.njobs, p.nsplit); cfg.dynamicSmemBytes = gram_smem_bytes(r.gram_stages);
             if (r.gram_threads == 512) {
                 cfg.blockDim = dim3(512);
                 MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_gram_evd_kernel<512>, p, rd, rd == 0 ? 1 : 0, r.gram_stages));
