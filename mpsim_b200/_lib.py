@@ -11,7 +11,8 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmpsim_b200.so")
+# MPSIM_B200_LIB: another build of the same library (A/B timing of kernel variants); no fallback either way
+LIB_PATH = os.environ.get("MPSIM_B200_LIB") or os.path.join(_HERE, "libmpsim_b200.so")
 
 MAX_SMALL_DIM = 128      # MPSB_MAX_SMALL_DIM of include/mpsim_b200.h
 

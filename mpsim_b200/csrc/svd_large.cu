@@ -23,7 +23,7 @@ constexpr int P = 32;            // rows per block pair
 constexpr int BLK = P / 2;       // rows per block
 constexpr int LT = 256;          // threads
 constexpr int CT = 128;          // columns per apply tile
-constexpr int MAX_OUTER = 40;
+constexpr int MAX_OUTER = 64;
 constexpr float ABS_ETA = 3e-7f;     // see bj_gram_evd_kernel
 
 struct Misc {                    // per job, lives in the workspace
@@ -158,9 +158,12 @@ constexpr int XS_LD = GK + 1;
 constexpr int GRAM_MAX_STAGES = 4;           // a small batch is bound by the latency of its tile loads: deeper ring
 constexpr int gram_smem_bytes(int nst) { return (nst * P * XS_LD + 2 * P * (P + 1)) * (int)sizeof(cf); }
 
-template <int NTHR>                          // 256, or 512 for launches with fewer CTAs than SMs (halves Gram and NS)
-__global__ void __launch_bounds__(NTHR) bj_gram_evd_kernel(LargeParams p, int round, int first_round, int nst) {
-    constexpr int NGRP = NTHR / 64, NWARP = NTHR / 32;
+// (ty | tx << 4) of the 36 thread tiles with ty <= tx (see bj_gram_evd_kernel)
+__constant__ unsigned char c_tri[36] = {0, 16, 32, 48, 64, 80, 96, 112, 17, 33, 49, 65, 81, 97, 113, 34, 50, 66, 82, 98, 114, 51, 67, 83, 99, 115, 68, 84, 100, 116, 85, 101, 117, 102, 118, 119};
+
+template <int NTHR, bool SYM>                // NTHR: 256 (512: timing experiments); SYM: see the Gram loop
+__global__ void __launch_bounds__(NTHR, NTHR == 512 ? 1 : 3) bj_gram_evd_kernel(LargeParams p, int round, int first_round, int nst) {
+    constexpr int NGS = SYM ? NTHR / 36 : NTHR / 64, NWARP = NTHR / 32;
     const int job = blockIdx.y, g = blockIdx.x;
     griddep_wait();
     if (!p.misc[job].active) return;
@@ -171,8 +174,20 @@ __global__ void __launch_bounds__(NTHR) bj_gram_evd_kernel(LargeParams p, int ro
     int I, J;
     pair_blocks(p.nb, round, g, I, J);
     const cf* X = p.X + (size_t)job * p.x_stride;
-    const int grp = threadIdx.x >> 6, t64 = threadIdx.x & 63;
-    const int tx = t64 & 7, ty = t64 >> 3;
+    // Thread tiles: 4 x 4 entries, rows ty + 8 i, columns tx + 8 j (conflict-free LDS); the threads
+    // of a group cover G once and the NGS groups share the columns of every staged tile.
+    // SYM: G is Hermitian, so only the 36 thread tiles with ty <= tx are computed, by NGS = 7
+    // groups of 36 threads, and the rest is mirrored afterwards: ~9 columns of 16 complex FMAs
+    // per thread and tile instead of 16 (this loop is FFMA-issue bound: 79 % of the issue slots in
+    // profiles/r1_svd_large_ncu_full.txt).  Measured: 50 x 512^2 194 -> 179 ms, 4 x 2048^2
+    // 1.02 -> 0.94 s, configs[2] 722 -> 766 applications/s.  CTAs that see a single tile (split
+    // Gram of one 256 x 256 matrix) keep the full 8 x 8 grid: the mirrored variant was 4 % slower
+    // there (8.14 -> 8.47 ms per solve).
+    constexpr int TPG = SYM ? 36 : 64;
+    const bool gact = threadIdx.x < NGS * TPG;
+    const int grp = threadIdx.x / TPG;
+    const int tyx = SYM ? c_tri[threadIdx.x % TPG] : ((threadIdx.x >> 3) & 7) | ((threadIdx.x & 7) << 4);
+    const int ty = tyx & 15, tx = tyx >> 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     auto issue = [&](int c0, cf* buf) {
         for (int e = threadIdx.x; e < P * GK; e += NTHR) {
@@ -202,9 +217,11 @@ __global__ void __launch_bounds__(NTHR) bj_gram_evd_kernel(LargeParams p, int ro
         else if (pending == 1) cp_async_wait<1>();
         else cp_async_wait<0>();
         __syncthreads();
-#pragma unroll 4
-        for (int cc = 0; cc < GK / NGRP; ++cc) {
-            const int c = grp * (GK / NGRP) + cc;
+#pragma unroll 2
+        for (int n = grp; n < (gact ? GK : 0); n += NGS) {
+            // SYM: column n of the tile in 8 x 8 transposed order -- the two groups that share a
+            // warp read columns 8 apart, i.e. the other half of the shared-memory banks (row stride 65)
+            const int c = SYM ? ((n & 7) << 3) | (n >> 3) : n;
             cf a[4], b[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) a[i] = Xs[(ty + 8 * i) * XS_LD + c];
@@ -218,17 +235,53 @@ __global__ void __launch_bounds__(NTHR) bj_gram_evd_kernel(LargeParams p, int ro
         __syncthreads();
     }
     BJ_CLK(1);
-    for (int q = 0; q < NGRP; ++q) {
-        if (grp == q) {
+    if (SYM && NGS * 36 * 16 <= nst * P * XS_LD) {       // block-uniform
+        // the partial tiles of the NGS groups go through the (now free) tile ring, laid out
+        // [group][tile entry][thread tile] so that a warp stores consecutive elements; every
+        // thread then adds the NGS partial sums of its G entries in a fixed order (one barrier
+        // instead of NGS) and the mirrored entries G[r][c] = conj(G[c][r]) are filled on the way
+        cf* part = Xbuf;
+        const int u36 = threadIdx.x % 36;
+        if (gact) {
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    cf& d = Gs[ty + 8 * i][tx + 8 * j];
-                    d = q == 0 ? acc[i][j] : cf_add(d, acc[i][j]);
-                }
+                for (int j = 0; j < 4; ++j) part[(grp * 16 + i * 4 + j) * 36 + u36] = acc[i][j];
         }
         __syncthreads();
+        for (int e = threadIdx.x; e < P * P; e += NTHR) {
+            const int r = e / P, c = e % P;
+            const bool up = (r & 7) <= (c & 7);
+            const int rr = up ? r : c, cc = up ? c : r;
+            const int ty_ = rr & 7, tx_ = cc & 7;
+            const int uu = ty_ * 8 - ty_ * (ty_ - 1) / 2 + (tx_ - ty_);
+            const int idx = (rr >> 3) * 4 + (cc >> 3);
+            cf sum = part[idx * 36 + uu];
+            for (int q = 1; q < NGS; ++q) sum = cf_add(sum, part[(q * 16 + idx) * 36 + uu]);
+            Gs[r][c] = up ? sum : cf_conj(sum);
+        }
+        __syncthreads();
+    } else {
+        for (int q = 0; q < NGS; ++q) {
+            if (grp == q) {                   // (threads beyond the last group have grp == NGS)
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        cf& d = Gs[ty + 8 * i][tx + 8 * j];
+                        d = q == 0 ? acc[i][j] : cf_add(d, acc[i][j]);
+                    }
+            }
+            __syncthreads();
+        }
+        if (SYM) {
+            // the other triangle of the thread-tile grid: G[r][c] = conj(G[c][r]) where (r mod 8) > (c mod 8)
+            for (int e = threadIdx.x; e < P * P; e += NTHR) {
+                const int r = e / P, c = e % P;
+                if ((r & 7) > (c & 7)) Gs[r][c] = cf_conj(Gs[c][r]);
+            }
+            __syncthreads();
+        }
     }
     if (p.nsplit > 1) {
         // A launch with fewer pairs than SMs (one or two matrices) spreads each pair's Gram over
@@ -738,8 +791,9 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
     static bool attrs = false;
     if (!attrs) {
         MPSB_CUDA(cudaFuncSetAttribute(bj_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, APPLY_SMEM));
-        MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes(GRAM_MAX_STAGES)));
-        MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes(GRAM_MAX_STAGES)));
+        MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes(GRAM_MAX_STAGES)));
+        MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes(GRAM_MAX_STAGES)));
+        MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes(GRAM_MAX_STAGES)));
         attrs = true;
     }
     // keep the input: the weighted factor is recomputed from it at the end (see large_finish)
@@ -765,10 +819,13 @@ static int large_enqueue_sweep(LargeRun& r) {
             cfg.gridDim = dim3(lo.npairs, r.njobs, p.nsplit); cfg.dynamicSmemBytes = gram_smem_bytes(r.gram_stages);
             if (r.gram_threads == 512) {
                 cfg.blockDim = dim3(512);
-                MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_gram_evd_kernel<512>, p, rd, rd == 0 ? 1 : 0, r.gram_stages));
+                MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_gram_evd_kernel<512, false>, p, rd, rd == 0 ? 1 : 0, r.gram_stages));
+            } else if (((p.L + GK - 1) / GK) / p.nsplit >= 2) {      // at least two column tiles per CTA
+                cfg.blockDim = dim3(256);
+                MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_gram_evd_kernel<256, true>, p, rd, rd == 0 ? 1 : 0, r.gram_stages));
             } else {
                 cfg.blockDim = dim3(256);
-                MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_gram_evd_kernel<256>, p, rd, rd == 0 ? 1 : 0, r.gram_stages));
+                MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_gram_evd_kernel<256, false>, p, rd, rd == 0 ? 1 : 0, r.gram_stages));
             }
         }
         if (!(r.skip & 4)) {
