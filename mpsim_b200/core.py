@@ -16,7 +16,7 @@ from typing import Any, Dict, List, Optional, Sequence, Tuple, Union
 import numpy as np
 
 from mpsim_b200 import gates as _gates
-from mpsim_b200.node import Node, tensor_of
+from mpsim_b200.node import BondEdge, Node, tensor_of
 from mpsim_b200.planner import Plan, max_bond_dimensions, plan_operations
 
 BITSTRING = Union[Sequence[int], str]
@@ -105,6 +105,8 @@ def _check_gate_edges(gate: Any, nfree: int, what: str) -> np.ndarray:
 class MPS:
     """Matrix product state on the GPU (``mpsim/core.py:159-1423``)."""
 
+    _last_bond_from_right = False        # graph-view detail (see _bond_edge); set by __init__
+
     def __init__(self, nqudits: int, qudit_dimension: int = 2, tensor_prefix: str = "q",
                  track_norms: bool = False, device: Any = None) -> None:
         if nqudits < 2:                                              # core.py:184-187
@@ -119,6 +121,7 @@ class MPS:
         self._norms: List[float] = []
         self._last = None            # last CompiledPlan (svals / status for inspection)
         self._record_svals = False
+        self._last_bond_from_right = self._nqudits >= 3      # graph-view detail, see _bond_edge
 
     @staticmethod
     def from_wavefunction(wavefunction: Any, nqudits: int, qudit_dimension: int = 2, tensor_prefix: str = "q",
@@ -175,6 +178,29 @@ class MPS:
 
     def get_nodes(self, copy: bool = True) -> List[Node]:
         return [self.get_node(i) for i in range(self._nqudits)]
+
+    def get_free_edge_of(self, node_index: int, copy: bool = True) -> BondEdge:      # core.py:443-451
+        """The physical (dangling) leg of a site."""
+        i = range(self._nqudits)[node_index]
+        return BondEdge(self, ("phys", i), self.get_node(i), None, self._qudit_dimension)
+
+    def _bond_edge(self, bond: int) -> BondEdge:
+        """Bond between sites ``bond`` and ``bond + 1``.  ``node1`` / ``node2`` follow the order in
+        which the reference connects the chain (``mpsim/core.py:220-229``): left site first, except
+        the last bond of a chain of three or more sites, which is connected from the right end --
+        until a two-site application re-creates it (``split_node`` puts the left factor first)."""
+        left, right = self.get_node(bond), self.get_node(bond + 1)
+        if self._last_bond_from_right and bond == self._nqudits - 2:
+            left, right = right, left
+        return BondEdge(self, ("bond", bond), left, right, self._chain.bonds[bond + 1])
+
+    def get_left_connected_edge_of(self, node_index: int) -> Optional[BondEdge]:      # core.py:453-466
+        i = range(self._nqudits)[node_index]
+        return None if i == 0 else self._bond_edge(i - 1)
+
+    def get_right_connected_edge_of(self, node_index: int) -> Optional[BondEdge]:     # core.py:468-481
+        i = range(self._nqudits)[node_index]
+        return None if i == self._nqudits - 1 else self._bond_edge(i)
 
     def site_tensor(self, index: int):
         """Device view of site ``index`` as a torch tensor [chi_left][d][chi_right]."""
@@ -239,6 +265,8 @@ class MPS:
         plan = plan_operations(self._nqudits, self._qudit_dimension, self._chain.bonds, ops)
         if not plan.order:
             return
+        if any(a.site == self._nqudits - 2 for a in plan.apps2):
+            self._last_bond_from_right = False
         if self._track_norms and plan.apps2:
             # the reference records the norm after EVERY adjacent application (core.py:1160-1161);
             # to reproduce that the plan is cut after each one
@@ -477,6 +505,7 @@ class MPS:
         new._max_bond_dimensions = list(self._max_bond_dimensions)
         new._track_norms, new._norms = self._track_norms, []
         new._last, new._record_svals = None, False
+        new._last_bond_from_right = self._last_bond_from_right
         return new
 
     def __str__(self) -> str:

@@ -71,6 +71,33 @@ class Node:
         return self.name
 
 
+class BondEdge:
+    """A leg of the chain seen through the reference's graph accessors (``mpsim/core.py:443-481``
+    return ``tn.Edge`` objects): a bond between two neighbouring sites, or the physical (dangling)
+    leg of one site.  A compatibility VIEW -- the device store has no graph -- carrying what the
+    reference's callers and tests read: ``node1`` / ``node2`` (host copies of the sites, with the
+    reference's names), ``is_dangling()``, ``dimension``, and equality of two views of one bond."""
+
+    def __init__(self, owner: Any, key: Any, node1: "Node", node2: Optional["Node"], dimension: int,
+                 name: str = "__unnamed_edge__") -> None:
+        self._owner, self._key = owner, key
+        self.node1, self.node2 = node1, node2
+        self.dimension = int(dimension)
+        self.name = name
+
+    def is_dangling(self) -> bool:
+        return self.node2 is None
+
+    def get_nodes(self) -> List[Optional["Node"]]:
+        return [self.node1, self.node2]
+
+    def __eq__(self, other: Any) -> bool:
+        return isinstance(other, BondEdge) and self._owner is other._owner and self._key == other._key
+
+    def __hash__(self) -> int:
+        return hash((id(self._owner), self._key))
+
+
 def tensor_of(gate: Any) -> np.ndarray:
     """The array of a gate given as ``Node``, ``tn.Node`` or a plain array."""
     if isinstance(gate, np.ndarray):

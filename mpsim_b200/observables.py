@@ -173,4 +173,5 @@ def from_wavefunction(cls, wavefunction: Any, nqudits: int, qudit_dimension: int
         rest = _device_matmul(torch.diag(inv).to(torch.complex64), svh)        # sqrt(S) Vh
         mps._chain.set_site(i, left.reshape(chi, d, -1), 0)
     mps._chain.set_site(nqudits - 1, rest.reshape(rest.shape[0], d, 1), 0)
+    mps._last_bond_from_right = False        # every bond comes out of a split, left factor first
     return mps

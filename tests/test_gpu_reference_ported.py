@@ -267,3 +267,39 @@ def test_equal_and_copy():                                       # core_test.py:
                 assert mps_copy == mps1
     assert mp.MPS(nqudits=10, qudit_dimension=2, tensor_prefix="mps1_") == \
         mp.MPS(nqudits=10, qudit_dimension=2, tensor_prefix="mps2_")
+
+
+def test_get_free_edge_of():                                     # core_test.py:165-173
+    MPS = _mp().MPS
+    for n in range(2, 10):
+        for d in (2, 3, 4):
+            mps = MPS(nqudits=n, qudit_dimension=d)
+            for i in range(n):
+                free_edge = mps.get_free_edge_of(i, copy=False)
+                assert free_edge.is_dangling()
+                assert free_edge.node1.name == f"q{i}"
+
+
+def test_get_left_and_right_connected_edges():                   # core_test.py:176-227
+    MPS = _mp().MPS
+    for d in (2, 3, 4):
+        mps = MPS(nqudits=3, qudit_dimension=d)
+        assert mps.get_left_connected_edge_of(0) is None
+        edge = mps.get_left_connected_edge_of(1)
+        assert not edge.is_dangling()
+        assert (edge.node1.name, edge.node2.name) == ("q0", "q1")
+        edge = mps.get_left_connected_edge_of(2)
+        assert not edge.is_dangling()
+        assert (edge.node1.name, edge.node2.name) == ("q2", "q1")
+        edge = mps.get_right_connected_edge_of(0)
+        assert not edge.is_dangling()
+        assert (edge.node1.name, edge.node2.name) == ("q0", "q1")
+        edge = mps.get_right_connected_edge_of(1)
+        assert not edge.is_dangling()
+        assert (edge.node1.name, edge.node2.name) == ("q2", "q1")
+        assert mps.get_right_connected_edge_of(2) is None
+    n = 10
+    for d in (2, 3, 4):
+        mps = MPS(nqudits=n, qudit_dimension=d)
+        for i in range(1, n - 1):
+            assert mps.get_right_connected_edge_of(i - 1) == mps.get_left_connected_edge_of(i)

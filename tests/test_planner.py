@@ -90,3 +90,37 @@ def test_shard_range():
             parts = [shard_range(total, r, world) for r in range(world)]
             assert parts[0][0] == 0 and parts[-1][1] == total
             assert all(parts[i][1] == parts[i + 1][0] for i in range(world - 1))
+
+
+def test_graph_edge_views_on_a_stub_chain():      # core_test.py:165-227 (the GPU port is in test_gpu_reference_ported.py)
+    """The reference's graph accessors are views computed from the chain's bookkeeping: check them
+    on a host stub of the device store (no kernels involved)."""
+    import torch
+    from mpsim_b200.core import MPS
+
+    class StubChain:
+        def __init__(self, n, d):
+            self.n, self.d = n, d
+            self.bonds = [1] * (n + 1)
+
+        def site_view(self, i, b=0):
+            t = torch.zeros((self.bonds[i], self.d, self.bonds[i + 1]), dtype=torch.complex64)
+            t[0, 0, 0] = 1
+            return t
+
+    for n in (2, 3, 6):
+        mps = MPS.__new__(MPS)
+        mps._nqudits, mps._qudit_dimension, mps._prefix = n, 3, "q"
+        mps._chain = StubChain(n, 3)
+        mps._last_bond_from_right = n >= 3
+        for i in range(n):
+            e = mps.get_free_edge_of(i, copy=False)
+            assert e.is_dangling() and e.node1.name == f"q{i}" and e.dimension == 3
+        assert mps.get_left_connected_edge_of(0) is None and mps.get_right_connected_edge_of(n - 1) is None
+        for i in range(1, n):
+            assert mps.get_right_connected_edge_of(i - 1) == mps.get_left_connected_edge_of(i)
+            assert mps.get_left_connected_edge_of(i) != mps.get_free_edge_of(i)
+        last = mps.get_left_connected_edge_of(n - 1)
+        names = (last.node1.name, last.node2.name)
+        assert names == ((f"q{n - 1}", f"q{n - 2}") if n >= 3 else ("q0", "q1"))
+        assert not last.is_dangling() and last.dimension == 1
