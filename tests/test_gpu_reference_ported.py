@@ -303,3 +303,107 @@ def test_get_left_and_right_connected_edges():                   # core_test.py:
         mps = MPS(nqudits=n, qudit_dimension=d)
         for i in range(1, n - 1):
             assert mps.get_right_connected_edge_of(i - 1) == mps.get_left_connected_edge_of(i)
+
+
+def _gates_mod():
+    """mpsim.gates of whichever package _mp() returns (the reference keeps them in mpsim.gates)."""
+    import importlib
+    return importlib.import_module(_mp().__name__ + ".gates")
+
+
+def test_mps_operation_properties():                             # core_test.py:25-67
+    mp, g = _mp(), _gates_mod()
+    op = mp.MPSOperation(g.igate(), qudit_indices=0, qudit_dimension=2)
+    assert op.qudit_indices == (0,) and op.qudit_dimension == 2
+    assert op.is_valid() and op.is_unitary()
+    assert op.is_single_qudit_operation() and not op.is_two_qudit_operation()
+
+    np.random.seed(1)
+    tensor = np.random.randn(2, 2)
+    node = type(g.igate())(tensor)
+    op = mp.MPSOperation(node, qudit_indices=(0,), qudit_dimension=2)
+    assert len(node.edges) == len(op.node(copy=True).edges)
+    assert _close(tensor, op.tensor())
+
+    op = mp.MPSOperation(g.cnot(), qudit_indices=(0, 1), qudit_dimension=2)
+    assert op.qudit_indices == (0, 1) and op.qudit_dimension == 2
+    assert not op.is_single_qudit_operation() and op.is_two_qudit_operation()
+
+    op = mp.MPSOperation(g.cnot(), qudit_indices=(0, 2), qudit_dimension=2)
+    assert op.qudit_indices == (0, 2) and op.is_valid()
+    assert not op.is_single_qudit_operation() and op.is_two_qudit_operation()
+
+
+@pytest.mark.parametrize("left", [True, False])
+def test_apply_twoq_cnot_four_qubits(left):                      # core_test.py:488-520
+    MPS = _mp().MPS
+    for prepare, cnot, index in (((1,), (1, 2), 6), ((), (1, 2), 0), ((2,), (2, 3), 3), ((0,), (0, 1), 12)):
+        mps = MPS(nqudits=4)
+        for q in prepare:
+            mps.x(q)
+        mps.cnot(*cnot, keep_left_canonical=left)
+        correct = np.zeros(16)
+        correct[index] = 1.0
+        assert _close(mps.wavefunction(), correct)
+
+
+@pytest.mark.parametrize("left", [True, False])
+def test_qubit_hopping_left_to_right(left):                      # core_test.py:618-628
+    n = 8
+    mps = _mp().MPS(n)
+    mps.h(0)
+    for i in range(1, n - 1):
+        mps.swap(i, i + 1, keep_left_canonical=left)
+    correct = np.zeros(2 ** n)
+    correct[0] = correct[2 ** (n - 1)] = 1.0 / np.sqrt(2)
+    assert _close(mps.wavefunction(), correct)
+
+
+def test_valid_after_orthonormalize_right_edges():               # core_test.py:1261-1285
+    mp, g = _mp(), _gates_mod()
+    n = 3
+    mps = mp.MPS(nqudits=n)
+    mps.apply([mp.MPSOperation(g.hgate(), (i,)) for i in range(n)])
+    before = mps.wavefunction()
+    assert [mps.bond_dimension_of(0), mps.bond_dimension_of(1)] == [1, 1]
+    for site in (0, 1):
+        mps.orthonormalize_right_edge_of(site)
+        assert mps.is_valid()
+        assert [mps.bond_dimension_of(0), mps.bond_dimension_of(1)] == [1, 1]
+        assert _close(mps.wavefunction(), before)
+
+
+def test_apply_povm_product_state():                             # core_test.py:1288-1338
+    mp, g = _mp(), _gates_mod()
+    pi0 = g.computational_basis_projector(state=0)
+    n = 3
+    mps = mp.MPS(nqudits=n)
+    mps.apply([mp.MPSOperation(g.hgate(), i) for i in range(n)])          # |+++>
+    assert np.isclose(mps.norm(), 1.0, atol=1e-6)
+    assert mps.bond_dimensions() == [1, 1]
+    for site in range(n):                   # |0><0| on one more qubit each time, nothing else
+        mps.apply_one_qudit_gate(pi0, site, ortho_after_non_unitary=False, renormalize_after_non_unitary=False)
+        assert mps.is_valid()
+        assert np.isclose(mps.norm(), np.sqrt(0.5) ** (site + 1), atol=1e-6)
+        assert mps.bond_dimensions() == [1, 1]
+        ones = 2 ** (n - 1 - site)
+        correct = np.sqrt(0.5) ** 3 * np.array([1] * ones + [0] * (8 - ones))
+        assert _close(mps.wavefunction(), correct)
+
+
+def test_orthonormalize_all_tensors_edge_cases():                # core_test.py:1431-1448
+    MPS = _mp().MPS
+    for n in range(2, 8):
+        for d in (2, 3, 4):
+            mps = MPS(nqudits=n, qudit_dimension=d)
+            correct = mps.wavefunction()
+            for site in range(n - 1):
+                mps.orthonormalize_right_edge_of(site)
+                assert mps.is_valid()
+                assert _close(mps.wavefunction(), correct)
+                assert np.isclose(mps.norm(), 1.0, atol=1e-6)
+            for site in range(1, n):
+                mps.orthonormalize_left_edge_of(site)
+                assert mps.is_valid()
+                assert _close(mps.wavefunction(), correct)
+                assert np.isclose(mps.norm(), 1.0, atol=1e-6)
