@@ -17,7 +17,7 @@ def needs_build() -> bool:
     if not os.path.exists(OUT):
         return True
     t = os.path.getmtime(OUT)
-    deps = [os.path.join(HERE, s) for s in SOURCES] + [os.path.join(HERE, "common.cuh"),
+    deps = [os.path.join(HERE, s) for s in SOURCES] + [os.path.join(HERE, "common.cuh"), os.path.join(HERE, "tc_ptx.cuh"),
             os.path.join(os.path.dirname(PKG), "include", "mpsim_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 

@@ -13,6 +13,7 @@
 // (mpsim/core.py:1132-1152).  Round 1: FFMA tiles; the Gram/apply steps are the candidates for
 // tcgen05 3xTF32.
 #include "common.cuh"
+#include "tc_ptx.cuh"
 #include <vector>
 #include <stdlib.h>
 #include <sched.h>
@@ -562,6 +563,234 @@ __global__ void __launch_bounds__(LT) bj_apply_kernel(LargeParams p, int round, 
     }
 }
 
+// ---- the same block rotation on the tensor cores (EXPERIMENTAL, MPSB_LARGE_TC_APPLY=1) ---------
+// Status: compiles for sm_100a; NOT yet run on hardware and not the default -- no claim is made
+// for it ("next step on this path").  bj_apply_kernel above is the product path.
+//
+// out[i][c] = sum_k Q[i][k] T[k][c] for the 32 rows of a pair and a tile of 128 columns, as ONE real
+// 3xTF32 product per tile with the columns of the tile as MMA rows:
+//   D[m][2i+u] = sum_kk A[m][kk] B[2i+u][kk],   m = column in the tile, kk = 2k + t  (K' = 64)
+//   A[m][2k+t]  = t ? Im T[k][m] : Re T[k][m]
+//   B[2i][2k] = Qr, B[2i][2k+1] = -Qi, B[2i+1][2k] = Qi, B[2i+1][2k+1] = Qr        (Q = Q[i][k])
+// so that row m of the accumulator is the interleaved complex column m of the output: TMEM lane m
+// stores out[i][c0+m] = (D[m][2i], D[m][2i+1]) for i = 0..31, a warp writing 256 contiguous bytes
+// per row.  M = 128, N = 64, K' = 64: 2 k-blocks x 4 k-steps x 3 operand pairings = 24
+// tcgen05.mma.kind::tf32 per tile (hi*lo + lo*hi + hi*hi, fp32 accumulation in TMEM).
+// The rows of X are contiguous along m, the MMA wants K-major operands, and 3xTF32 needs the
+// hi/lo split: the loader warps read the tile from global memory (coalesced), split it in
+// registers and write A_hi / A_lo straight into the canonical K-major SWIZZLE_128B layout that TMA
+// would produce (row m at m * 128 bytes, 16-byte chunk j stored at j ^ (m & 7)), then
+// fence.proxy.async + mbarrier.  A separate split pass through HBM would triple the traffic of a
+// round; this way a tile is read once and written once (64 KB per tile and SM: HBM bound).
+// Roles (416 threads, persistent, one CTA per SM, contiguous range of (job, pair, tile) items per
+// CTA so that B = the embedding of Q is rebuilt only when the pair changes):
+//   warps 0-3  epilogue: tcgen05.ld of the 64 accumulator columns of lane m, global stores;
+//   warp  4    MMA issuer (one lane), two 64-column accumulators in TMEM so that the drain of a
+//              tile overlaps the MMAs of the next;
+//   warps 5-12 loaders / splitters, 2-stage ring of 96 KB stages (A_hi, A_lo, B_hi, B_lo).
+constexpr int TA_M = 128;                               // columns per tile = MMA rows (TMEM lanes)
+constexpr int TA_N = 2 * P;                             // 64 accumulator columns: (i, re | im)
+constexpr int TA_KB_A = TA_M * 128;                     // bytes of one k-block (32 fp32) of A
+constexpr int TA_KB_B = TA_N * 128;                     // ... of B
+constexpr int TA_A_BYTES = 2 * TA_KB_A;                 // K' = 64 fp32 = 2 k-blocks
+constexpr int TA_B_BYTES = 2 * TA_KB_B;
+constexpr int TA_STAGE_BYTES = 2 * TA_A_BYTES + 2 * TA_B_BYTES;     // 96 KB
+constexpr int TA_STAGES = 2;
+constexpr int TA_SMEM = TA_STAGES * TA_STAGE_BYTES + 1024;           // + slack to align the ring to 1024
+constexpr int TA_EPI_WARPS = 4, TA_LOAD_WARPS = 8;
+constexpr int TA_LOAD_THREADS = TA_LOAD_WARPS * 32;
+constexpr int TA_THREADS = (TA_EPI_WARPS + 1 + TA_LOAD_WARPS) * 32;
+static_assert(CT == TA_M, "the tensor-core apply uses the tile width of bj_apply_kernel");
+
+struct TaItem { int job, g, tile; bool skip; };
+
+__device__ __forceinline__ TaItem ta_item(const LargeParams& p, long long it, int ntot) {
+    TaItem w;
+    const long long pr = it / ntot;
+    w.tile = (int)(it - pr * ntot);
+    w.job = (int)(pr / p.npairs);
+    w.g = (int)(pr - (long long)w.job * p.npairs);
+    w.skip = !p.misc[w.job].active || !p.rotflag[pr];
+    return w;
+}
+
+// byte offset of the (re, im) pair of pair-row k in row r of a K-major SWIZZLE_128B operand
+__device__ __forceinline__ int ta_offset(int r, int k, int kb_bytes) {
+    return (k >> 4) * kb_bytes + r * 128 + ((((k & 15) >> 1) ^ (r & 7)) << 4) + ((k & 1) << 3);
+}
+
+__global__ void __launch_bounds__(TA_THREADS, 1) bj_apply_tc_kernel(LargeParams p, int round, int ntx, int ntot, int njobs) {
+    using namespace tcx;
+    extern __shared__ __align__(1024) uint8_t ta_smem[];
+    __shared__ __align__(8) uint64_t full_bar[TA_STAGES], empty_bar[TA_STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+    uint8_t* ring = (uint8_t*)(((uintptr_t)ta_smem + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    griddep_wait();
+    if (warp == TA_EPI_WARPS && lane == 0) {
+        for (int s = 0; s < TA_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], TA_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(2u * TA_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    const long long total = (long long)njobs * p.npairs * ntot;
+    const long long per = (total + gridDim.x - 1) / gridDim.x;
+    const long long it0 = per * blockIdx.x, it1 = min(total, it0 + per);
+
+    if (warp > TA_EPI_WARPS) {
+        // ===== loaders: global -> registers (hi/lo split) -> swizzled K-major operands =====
+        const int lt = threadIdx.x - (TA_EPI_WARPS + 1) * 32, lw = lt >> 5;
+        long long held0 = -1, held1 = -1;                  // pair whose B each stage holds
+        int n = 0;
+        for (long long it = it0; it < it1; ++it) {
+            const TaItem w = ta_item(p, it, ntot);
+            if (w.skip) continue;
+            const int s = n & 1;
+            uint8_t* st = ring + (size_t)s * TA_STAGE_BYTES;
+            int I, J;
+            pair_blocks(p.nb, round, w.g, I, J);
+            const cf* base; int ld, c0, ncol;
+            if (w.tile < ntx) { base = p.X + (size_t)w.job * p.x_stride; ld = p.L; c0 = w.tile * TA_M; ncol = p.L; }
+            else { base = p.Z + (size_t)w.job * p.z_stride; ld = p.nvp; c0 = (w.tile - ntx) * TA_M; ncol = p.nvp; }
+            // all 16 loads of this thread first (the shared-memory stores below may alias them as far as
+            // the compiler knows: interleaved, every load waited for the previous store -- 8 us per tile)
+            constexpr int RPW = P / TA_LOAD_WARPS, CPL = TA_M / 32;
+            cf v[RPW][CPL];
+#pragma unroll
+            for (int rr = 0; rr < RPW; ++rr) {
+                const cf* row = base + (size_t)pair_row(I, J, lw * RPW + rr) * ld + c0;
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) v[rr][j] = c0 + lane + 32 * j < ncol ? __ldcg(row + lane + 32 * j) : cf_make(0.f, 0.f);
+            }
+            const long long pr = (long long)w.job * p.npairs + w.g;
+            const bool newq = (s ? held1 : held0) != pr;
+            cf qv[P * P / TA_LOAD_THREADS];
+            if (newq) {
+                const cf* Q = p.Q + (size_t)w.job * p.g_stride + (size_t)w.g * P * P;
+#pragma unroll
+                for (int j = 0; j < P * P / TA_LOAD_THREADS; ++j) qv[j] = __ldcg(Q + lt + TA_LOAD_THREADS * j);
+            }
+            mbar_wait(&empty_bar[s], ((n >> 1) & 1) ^ 1);    // (the loads above are in flight while the stage drains)
+#pragma unroll
+            for (int rr = 0; rr < RPW; ++rr) {
+                const int k = lw * RPW + rr;
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    const int m = lane + 32 * j;
+                    float rh, rl, ih, il;
+                    split_tf32(v[rr][j].x, rh, rl);
+                    split_tf32(v[rr][j].y, ih, il);
+                    const int off = ta_offset(m, k, TA_KB_A);
+                    *reinterpret_cast<float2*>(st + off) = make_float2(rh, ih);
+                    *reinterpret_cast<float2*>(st + TA_A_BYTES + off) = make_float2(rl, il);
+                }
+            }
+            if (newq) {
+                if (s) held1 = pr; else held0 = pr;
+                uint8_t* bh = st + 2 * TA_A_BYTES;
+                uint8_t* bl = bh + TA_B_BYTES;
+#pragma unroll
+                for (int j = 0; j < P * P / TA_LOAD_THREADS; ++j) {
+                    const int e = lt + TA_LOAD_THREADS * j, i = e >> 5, k = e & 31;
+                    float rh, rl, ih, il;
+                    split_tf32(qv[j].x, rh, rl);
+                    split_tf32(qv[j].y, ih, il);
+                    const int o0 = ta_offset(2 * i, k, TA_KB_B), o1 = ta_offset(2 * i + 1, k, TA_KB_B);
+                    *reinterpret_cast<float2*>(bh + o0) = make_float2(rh, -ih);
+                    *reinterpret_cast<float2*>(bl + o0) = make_float2(rl, -il);
+                    *reinterpret_cast<float2*>(bh + o1) = make_float2(ih, rh);
+                    *reinterpret_cast<float2*>(bl + o1) = make_float2(il, rl);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> UMMA reads
+            named_bar_sync(1, TA_LOAD_THREADS);
+            if (lt == 0) mbar_arrive(&full_bar[s]);
+            ++n;
+        }
+    } else if (warp == TA_EPI_WARPS) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_tf32(TA_M, TA_N);
+            int n = 0;
+            for (long long it = it0; it < it1; ++it) {
+                if (ta_item(p, it, ntot).skip) continue;
+                const int s = n & 1;
+                const uint32_t ph = (n >> 1) & 1;
+                mbar_wait(&acc_empty[s], ph ^ 1);
+                mbar_wait(&full_bar[s], ph);
+                tc_fence_after();
+                const uint32_t sa = smem_u32(ring + (size_t)s * TA_STAGE_BYTES);
+                const uint32_t tmem_d = tmem_base + (uint32_t)s * TA_N;
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    const uint64_t ahi = umma_desc_k128(sa + kb * TA_KB_A), alo = umma_desc_k128(sa + TA_A_BYTES + kb * TA_KB_A);
+                    const uint64_t bhi = umma_desc_k128(sa + 2 * TA_A_BYTES + kb * TA_KB_B);
+                    const uint64_t blo = umma_desc_k128(sa + 2 * TA_A_BYTES + TA_B_BYTES + kb * TA_KB_B);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t adv = (uint64_t)((ks * 32) >> 4);      // 8 tf32 = 32 bytes along K inside the swizzle row
+                        tc_mma_tf32(tmem_d, ahi + adv, blo + adv, idesc, (kb | ks) != 0);
+                        tc_mma_tf32(tmem_d, alo + adv, bhi + adv, idesc, 1);
+                        tc_mma_tf32(tmem_d, ahi + adv, bhi + adv, idesc, 1);
+                    }
+                }
+                tc_commit(&empty_bar[s]);
+                tc_commit(&acc_full[s]);
+                ++n;
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM lane m = column c0 + m of the tile =====
+        int n = 0;
+        for (long long it = it0; it < it1; ++it) {
+            const TaItem w = ta_item(p, it, ntot);
+            if (w.skip) continue;
+            const int a = n & 1;
+            mbar_wait(&acc_full[a], (n >> 1) & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + (uint32_t)a * TA_N + ((uint32_t)(warp * 32) << 16);
+            float d[TA_N];
+#pragma unroll
+            for (int c = 0; c < TA_N / 16; ++c) {
+                float v[16];
+                tc_ld16(trow + c * 16, v);
+                tc_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) d[c * 16 + i] = v[i];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
+            int I, J;
+            pair_blocks(p.nb, round, w.g, I, J);
+            cf* base; int ld, c0, ncol;
+            if (w.tile < ntx) { base = p.X + (size_t)w.job * p.x_stride; ld = p.L; c0 = w.tile * TA_M; ncol = p.L; }
+            else { base = p.Z + (size_t)w.job * p.z_stride; ld = p.nvp; c0 = (w.tile - ntx) * TA_M; ncol = p.nvp; }
+            const int col = c0 + warp * 32 + lane;
+            if (col < ncol) {
+#pragma unroll
+                for (int i = 0; i < P; ++i) base[(size_t)pair_row(I, J, i) * ld + col] = cf_make(d[2 * i], d[2 * i + 1]);
+            }
+            ++n;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * TA_N) : "memory");
+    }
+}
+
 // R <- 3/2 I - 1/2 R   (Newton-Schulz factor)
 __global__ void bj_ns_kernel(cf* R, int64_t stride, int n) {
     cf* r = R + (size_t)blockIdx.y * stride;
@@ -694,7 +923,7 @@ struct LargeRun {
     LargeLayout lo;
     OutParams o;
     cf *Rbuf, *Z2, *M0;
-    int njobs, nv, L, nrounds, ntx, ntz, max_outer, skip, nt_cta, pdl, gram_stages, gram_threads;
+    int njobs, nv, L, nrounds, ntx, ntz, max_outer, skip, nt_cta, pdl, gram_stages, gram_threads, tc_apply;
     cudaStream_t st;
     PinSlot* pin;
     int sweeps_queued = 0;
@@ -771,6 +1000,10 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
     r.pdl = 1;
     if (const char* e = getenv("MPSB_LARGE_NT")) r.nt_cta = atoi(e) > 0 ? atoi(e) : r.nt_cta;   // timing experiments only
     if (const char* e = getenv("MPSB_LARGE_PDL")) r.pdl = atoi(e);
+    // the tensor-core apply (bj_apply_tc_kernel) is persistent, one CTA per SM: taken when there are
+    // at least two tiles per SM, otherwise the FFMA kernel (a single 256 x 256 matrix is 32 tiles)
+    r.tc_apply = (long long)njobs * lo.npairs * (r.ntx + r.ntz) >= 2 * 148;
+    if (const char* e = getenv("MPSB_LARGE_TC_APPLY")) r.tc_apply = atoi(e) != 0;       // A/B timing
     r.skip = 0; r.max_outer = MAX_OUTER;
     if (const char* e = getenv("MPSB_LARGE_SKIP")) r.skip = atoi(e);
     if (const char* e = getenv("MPSB_LARGE_SWEEPS")) r.max_outer = atoi(e);
@@ -791,6 +1024,7 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
     static bool attrs = false;
     if (!attrs) {
         MPSB_CUDA(cudaFuncSetAttribute(bj_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, APPLY_SMEM));
+        MPSB_CUDA(cudaFuncSetAttribute(bj_apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
         MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes(GRAM_MAX_STAGES)));
         MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes(GRAM_MAX_STAGES)));
         MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes(GRAM_MAX_STAGES)));
@@ -828,7 +1062,12 @@ static int large_enqueue_sweep(LargeRun& r) {
                 MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_gram_evd_kernel<256, false>, p, rd, rd == 0 ? 1 : 0, r.gram_stages));
             }
         }
-        if (!(r.skip & 4)) {
+        if (!(r.skip & 4) && r.tc_apply) {
+            const long long items = (long long)r.njobs * lo.npairs * (r.ntx + r.ntz);
+            cfg.gridDim = dim3((unsigned)(items < 148 ? items : 148));
+            cfg.blockDim = dim3(TA_THREADS); cfg.dynamicSmemBytes = TA_SMEM;
+            MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_apply_tc_kernel, p, rd, r.ntx, r.ntx + r.ntz, r.njobs));
+        } else if (!(r.skip & 4)) {
             cfg.gridDim = dim3((r.ntx + r.ntz + r.nt_cta - 1) / r.nt_cta, lo.npairs, r.njobs);
             cfg.blockDim = dim3(LT); cfg.dynamicSmemBytes = APPLY_SMEM;
             MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_apply_kernel, p, rd, r.ntx, r.ntx + r.ntz, r.nt_cta));
