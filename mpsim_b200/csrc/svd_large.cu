@@ -10,8 +10,8 @@
 //     bj_apply    : Xp <- Q Xp,  Zp <- Q Zp            (P x P) . (P x (L + nv)), in place
 //   a job stops rotating (its launches become no-ops) after a sweep in which no pair rotated.
 // Replaces tn.split_node_full_svd -> np.linalg.svd for 2chi in {256, 512, 2048}
-// (mpsim/core.py:1132-1152).  Round 1: FFMA tiles; the Gram/apply steps are the candidates for
-// tcgen05 3xTF32.
+// (mpsim/core.py:1132-1152).  The Gram step runs on FFMA tiles; the apply on tcgen05 3xTF32 for
+// full launches (bj_apply_tc_kernel) and on FFMA tiles for one- and two-matrix launches.
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <vector>
@@ -563,9 +563,12 @@ __global__ void __launch_bounds__(LT) bj_apply_kernel(LargeParams p, int round, 
     }
 }
 
-// ---- the same block rotation on the tensor cores (EXPERIMENTAL, MPSB_LARGE_TC_APPLY=1) ---------
-// Status: compiles for sm_100a; NOT yet run on hardware and not the default -- no claim is made
-// for it ("next step on this path").  bj_apply_kernel above is the product path.
+// ---- the same block rotation on the tensor cores ----------------------------------------------
+// The apply of launches with at least two tiles per SM (large_begin; MPSB_LARGE_TC_APPLY=0/1 forces
+// the choice for A/B timing); bj_apply_kernel above serves the one- and two-matrix launches.
+// Measured on B200 (profiles/r1_tc_apply_runs.txt): 50 x 512^2 178 -> 145 ms per solve batch (the
+// apply itself 0.198 -> ~0.093 ms per round), configs[2] 766 -> 892 applications/s; all GPU parity
+// tests green with it (sigma within 1e-6 sigma_max of LAPACK at 512^2, 5e-6 at 2048^2).
 //
 // out[i][c] = sum_k Q[i][k] T[k][c] for the 32 rows of a pair and a tile of 128 columns, as ONE real
 // 3xTF32 product per tile with the columns of the tile as MMA rows:
