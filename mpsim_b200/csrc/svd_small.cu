@@ -181,14 +181,6 @@ __device__ __forceinline__ int threads_per_col(int ncols) {
     return t;
 }
 
-__device__ __forceinline__ cf group_sum(cf w, int tpc) {
-    for (int o = tpc >> 1; o > 0; o >>= 1) {
-        w.x += __shfl_xor_sync(0xffffffffu, w.x, o);
-        w.y += __shfl_xor_sync(0xffffffffu, w.y, o);
-    }
-    return w;
-}
-
 // Householder reduction of A [nrows][ncols] (row stride LS), register resident: tpc threads share
 // a column (thread (col, sub) keeps rows sub, sub + tpc, ... of its column in registers for the
 // whole factorisation), so a step only moves one column through shared memory (the first
