@@ -239,3 +239,13 @@ def test_svd_large_matches_lapack(shape, lc):
         err = np.linalg.norm(left[j] @ right[j] - best) / np.linalg.norm(best)
         assert err < 2e-3, err
         assert abs(np.linalg.norm(left[j] @ right[j]) - np.linalg.norm(best)) < 1e-5 * np.linalg.norm(best)
+
+
+@pytest.mark.parametrize("tc", [0, 1])
+@pytest.mark.parametrize("shape", [(512, 512), (200, 136), (130, 300)])
+def test_svd_large_both_apply_kernels(monkeypatch, shape, tc):
+    """The block rotation is applied by bj_apply_kernel (FFMA) or bj_apply_tc_kernel (tcgen05 3xTF32)
+    depending on the launch size; two matrices would always take the first.  Force each in turn
+    (the library reads the switch at call time) and hold both to the LAPACK bounds above."""
+    monkeypatch.setenv("MPSB_LARGE_TC_APPLY", str(tc))
+    test_svd_large_matches_lapack(shape, 1)
