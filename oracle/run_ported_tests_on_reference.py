@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE (build container only: needs /root/reference).
 
-Runs tests/test_gpu_reference_ported.py -- the reference's own tests ported to the GPU API -- against
-the UNMODIFIED reference package on oracle/tn_shim instead of mpsim_b200, on the CPU.  A port that
+Runs tests/test_gpu_reference_ported.py and tests/test_gates_ported.py -- the reference's own tests
+ported to this package's API -- against the UNMODIFIED reference package on oracle/tn_shim instead of mpsim_b200, on the CPU.  A port that
 does not hold on the reference itself is a wrong port; this is how the ports are checked before they
 are trusted as parity tests on the GPU.  (mpsim_cirq is left out: it needs the real Cirq.)
 
@@ -38,10 +38,14 @@ def main() -> int:
         sys.path[:0] = [os.path.join(HERE, "tn_shim"), tmp, ROOT]
         warnings.simplefilter("ignore")
         import mpsim
+        import mpsim.gates
         import tests.test_gpu_reference_ported as ported
+        import tests.test_gates_ported as gates_ported
         ported._mp = lambda: mpsim
+        gates_ported._g = lambda: mpsim.gates
         ok = bad = 0
-        for name, fn in inspect.getmembers(ported, inspect.isfunction):
+        cases = [(n, f) for mod in (ported, gates_ported) for n, f in inspect.getmembers(mod, inspect.isfunction)]
+        for name, fn in cases:
             if not name.startswith("test_"):
                 continue
             combos = [{}]
