@@ -26,14 +26,18 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + \
-          [os.path.join(HERE, s) for s in SOURCES] + ["-o", OUT]
+    # MPSB_NVCC_EXTRA / MPSB_LIB_OUT: variant builds for A/B timing (scripts/ab_large.sh), e.g.
+    #   MPSB_NVCC_EXTRA=-DTA_STS=1 MPSB_LIB_OUT=mpsim_b200/libmpsim_b200_sts.so python -m mpsim_b200.csrc.build
+    extra = os.environ.get("MPSB_NVCC_EXTRA", "").split()
+    out = os.environ.get("MPSB_LIB_OUT") or OUT
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + \
+          [os.path.join(HERE, s) for s in SOURCES] + ["-o", out]
     res = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if verbose or res.returncode != 0:
         sys.stderr.write(res.stdout)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed building libmpsim_b200.so")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":

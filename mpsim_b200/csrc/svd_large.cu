@@ -617,6 +617,20 @@ __device__ __forceinline__ TaItem ta_item(const LargeParams& p, long long it, in
     return w;
 }
 
+// Operand stores of the loader warps.  The compiler emits generic ST.E.64 for them (the ring pointer
+// is derived from an aligned cast); building with -DTA_STS=1 (MPSB_NVCC_EXTRA, csrc/build.py) uses
+// explicit st.shared.v2.f32 instead -- a variant to A/B on hardware, not yet measured.
+#ifndef TA_STS
+#define TA_STS 0
+#endif
+__device__ __forceinline__ void ta_store(uint8_t* base, int off, float a, float b) {
+#if TA_STS
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(tcx::smem_u32(base) + (uint32_t)off), "f"(a), "f"(b) : "memory");
+#else
+    *reinterpret_cast<float2*>(base + off) = make_float2(a, b);
+#endif
+}
+
 // byte offset of the (re, im) pair of pair-row k in row r of a K-major SWIZZLE_128B operand
 __device__ __forceinline__ int ta_offset(int r, int k, int kb_bytes) {
     return (k >> 4) * kb_bytes + r * 128 + ((((k & 15) >> 1) ^ (r & 7)) << 4) + ((k & 1) << 3);
@@ -693,8 +707,8 @@ __global__ void __launch_bounds__(TA_THREADS, 1) bj_apply_tc_kernel(LargeParams 
                     split_tf32(v[rr][j].x, rh, rl);
                     split_tf32(v[rr][j].y, ih, il);
                     const int off = ta_offset(m, k, TA_KB_A);
-                    *reinterpret_cast<float2*>(st + off) = make_float2(rh, ih);
-                    *reinterpret_cast<float2*>(st + TA_A_BYTES + off) = make_float2(rl, il);
+                    ta_store(st, off, rh, ih);
+                    ta_store(st + TA_A_BYTES, off, rl, il);
                 }
             }
             if (newq) {
@@ -708,10 +722,10 @@ __global__ void __launch_bounds__(TA_THREADS, 1) bj_apply_tc_kernel(LargeParams 
                     split_tf32(qv[j].x, rh, rl);
                     split_tf32(qv[j].y, ih, il);
                     const int o0 = ta_offset(2 * i, k, TA_KB_B), o1 = ta_offset(2 * i + 1, k, TA_KB_B);
-                    *reinterpret_cast<float2*>(bh + o0) = make_float2(rh, -ih);
-                    *reinterpret_cast<float2*>(bl + o0) = make_float2(rl, -il);
-                    *reinterpret_cast<float2*>(bh + o1) = make_float2(ih, rh);
-                    *reinterpret_cast<float2*>(bl + o1) = make_float2(il, rl);
+                    ta_store(bh, o0, rh, -ih);
+                    ta_store(bl, o0, rl, -il);
+                    ta_store(bh, o1, ih, rh);
+                    ta_store(bl, o1, il, rl);
                 }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> UMMA reads
