@@ -623,6 +623,16 @@ __device__ __forceinline__ TaItem ta_item(const LargeParams& p, long long it, in
 #ifndef TA_STS
 #define TA_STS 0
 #endif
+// -DTA_DELTA=1 (variant, not yet measured): the tensor cores compute (Q - I) T and the epilogue adds
+// T in fp32.  The accumulator truncates toward zero once per accumulating MMA; with Q itself the
+// dominant term q_ii t_i sits in the accumulator while ~12 more MMAs are added, a systematic shrink
+// of ~3e-7 per apply (x several thousand applies per solve, removed at the end by the
+// Newton-Schulz step on Z).  With Q - I only the O(angle) correction is accumulated, so the
+// truncation error scales with the rotation angle and vanishes as the sweeps converge; the price
+// is one read of the tile by the epilogue threads (L2 hits: the loaders just fetched it).
+#ifndef TA_DELTA
+#define TA_DELTA 0
+#endif
 __device__ __forceinline__ void ta_store(uint8_t* base, int off, float a, float b) {
 #if TA_STS
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(tcx::smem_u32(base) + (uint32_t)off), "f"(a), "f"(b) : "memory");
@@ -719,7 +729,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) bj_apply_tc_kernel(LargeParams 
                 for (int j = 0; j < P * P / TA_LOAD_THREADS; ++j) {
                     const int e = lt + TA_LOAD_THREADS * j, i = e >> 5, k = e & 31;
                     float rh, rl, ih, il;
-                    split_tf32(qv[j].x, rh, rl);
+                    split_tf32(qv[j].x - (TA_DELTA && i == k ? 1.0f : 0.0f), rh, rl);      // TA_DELTA: Q - I
                     split_tf32(qv[j].y, ih, il);
                     const int o0 = ta_offset(2 * i, k, TA_KB_B), o1 = ta_offset(2 * i + 1, k, TA_KB_B);
                     ta_store(bh, o0, rh, -ih);
@@ -795,7 +805,15 @@ __global__ void __launch_bounds__(TA_THREADS, 1) bj_apply_tc_kernel(LargeParams 
             const int col = c0 + warp * 32 + lane;
             if (col < ncol) {
 #pragma unroll
-                for (int i = 0; i < P; ++i) base[(size_t)pair_row(I, J, i) * ld + col] = cf_make(d[2 * i], d[2 * i + 1]);
+                for (int i = 0; i < P; ++i) {
+                    cf* dst = base + (size_t)pair_row(I, J, i) * ld + col;
+#if TA_DELTA
+                    const cf t = __ldcg(dst);                    // this thread owns (i, col): no hazard
+                    *dst = cf_make(t.x + d[2 * i], t.y + d[2 * i + 1]);
+#else
+                    *dst = cf_make(d[2 * i], d[2 * i + 1]);
+#endif
+                }
             }
             ++n;
         }
