@@ -43,6 +43,30 @@ def brickwork(nqubits: int, depth: int, seed: int) -> List[Op]:
     return ops
 
 
+def haar_gate_stack(count: int, rng: "np.random.Generator") -> np.ndarray:
+    """``count`` Haar-random 4x4 unitaries (Mezzadri, ``mpsim/gates.py:269-286``) drawn in one
+    vectorised call from a ``np.random.Generator``; shape ``(count, 4, 4)`` complex64."""
+    z = (rng.standard_normal((count, 4, 4)) + 1j * rng.standard_normal((count, 4, 4))) / np.sqrt(2)
+    q, r = np.linalg.qr(z)
+    dg = np.diagonal(r, axis1=1, axis2=2)
+    return (q * (dg / np.abs(dg))[:, None, :]).astype(np.complex64)
+
+
+def batch_member_gates(nops: int, member: int) -> np.ndarray:
+    """Gates of circuit ``member`` of the batched workload (BASELINE.json configs[3]): the
+    stream seeded ``1000 + member``; shape ``(nops, 16)`` complex64.  ``bench.py``'s GPU arm, its
+    CPU arms and the golden fixtures all take their gates from here."""
+    return haar_gate_stack(nops, np.random.default_rng(1000 + member)).reshape(nops, 16)
+
+
+def brickwork_member(nqubits: int, depth: int, member: int) -> List[Op]:
+    """Circuit ``member`` of the batched workload: the brickwork layer pattern of
+    :func:`brickwork` with the gates of :func:`batch_member_gates`."""
+    structure = brickwork(nqubits, depth, seed=0)
+    gates = batch_member_gates(len(structure), member)
+    return [Op(gates[t].reshape(2, 2, 2, 2), op.indices, op.keep_left_canonical) for t, op in enumerate(structure)]
+
+
 def ghz(nqubits: int) -> List[Op]:
     """H(0) then CNOT(0, i), i = 1..n-1 (``mpsim/core_test.py:1236-1245``)."""
     ops = [Op(_gates.hgate().tensor, (0,))]
@@ -109,6 +133,18 @@ def sycamore_snake(rows: int = 6, cols: int = 9, drop_last: int = 1, cycles: int
         for (i, j) in couplers(pattern[cyc % len(pattern)]):
             ops.append(Op(haar_two_qubit(rng), (i, j), True))
     return nq, ops
+
+
+def grid_snake(rows: int, cols: int, warmup_depth: int, cycles: int, seed: int) -> Tuple[int, List[Op]]:
+    """A small full-rank relative of :func:`sycamore_snake` for parity fixtures: ``warmup_depth``
+    brickwork layers of Haar gates first (they saturate every bond, so that no later theta is
+    rank deficient and the reference's result is well defined -- DESIGN.md section 2), then ``cycles``
+    cycles of the ABCD coupler pattern on the snake-ordered ``rows x cols`` grid, whose vertical
+    couplers are routed through swap networks."""
+    nq = rows * cols
+    ops = brickwork(nq, warmup_depth, seed)
+    _, tail = sycamore_snake(rows, cols, 0, cycles, seed + 1)
+    return nq, ops + tail
 
 
 def count_adjacent_applications(ops: Sequence[Op]) -> int:

@@ -277,8 +277,16 @@ class MPS:
         self._last = cp
 
     def _execute_tracking(self, plan: Plan, ops) -> None:
+        """One compiled step per application so that the norm can be read in between.  Order of the
+        recorded norms = the reference's: every SWAP of a swap network is itself an
+        ``apply_two_qudit_gate`` call and appends its norm, while the routed gate appends only after
+        its swap-back (``mpsim/core.py:1154-1161``) -- i.e. once more on the final state."""
         d = self._qudit_dimension
-        for kind, idx in plan.order:
+        last_of_op: Dict[int, int] = {}
+        for pos, (kind, idx) in enumerate(plan.order):
+            if kind == 2:
+                last_of_op[plan.apps2[idx].source_op] = pos
+        for pos, (kind, idx) in enumerate(plan.order):
             sub = Plan(self._nqudits, d, self._chain.bonds)
             if kind == 1:
                 a = plan.apps1[idx]
@@ -291,7 +299,11 @@ class MPS:
             self._chain.run(cp)
             self._last = cp
             if kind == 2:
-                self._norms.append(self.norm())
+                routed = last_of_op[a.source_op] != pos or a.is_swap     # part of a swap network
+                if a.is_swap or not routed:
+                    self._norms.append(self.norm())
+                if routed and last_of_op[a.source_op] == pos:
+                    self._norms.append(self.norm())                      # the routed gate's own entry
 
     def apply_one_qudit_gate(self, gate: Any, node_index: int, **kwargs: Any) -> None:
         """``mpsim/core.py:753-845``.  Unitary gates run entirely on the device; the non-unitary

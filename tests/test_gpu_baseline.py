@@ -1,0 +1,126 @@
+"""Reference-matching results AT THE SIZES BASELINE.json NAMES, on the GPU through the C-ABI, against the
+committed golden vectors of tests/golden/baseline/ (complex128 oracle, cross-checked there against the
+unmodified reference wherever the reference finishes in minutes -- tests/golden/make_golden_baseline.py):
+
+* configs[3]: members 0 and 511 of the 4096-circuit batch (40 qubits, depth 20, chi = 64, the gates
+  bench.py uses), run as ONE batch like the benchmark does;
+* configs[2] in full: 100 qubits, depth 20, chi = 256 (456 thetas of 512 x 512 on the block-Jacobi path);
+* a full-rank swap-network circuit on the block-Jacobi path (snake-ordered 4 x 4 grid, chi = 96).
+
+North-star tolerances, written out: kept counts exact; every singular value within 1e-5 of the
+application's largest AND every kept value >= 1e-3 sigma_max within 1e-5 of itself; where the full
+wavefunction exists, amplitudes within 1e-4 absolute and fidelity >= 1 - 1e-5.  At 40 / 100 qubits no
+wavefunction exists: 256 amplitudes at seeded bitstrings are compared relative to their own scale
+(sampled fidelity >= 1 - 1e-5, every sampled amplitude within 1e-2 of the rms amplitude) and the norm
+to 1e-4 relative.  For scale: the REFERENCE ITSELF, handed complex64 gates, stays in complex64 and its
+singular values are 2e-5 ... 2e-4 sigma_max away from these vectors (stored in the fixtures)."""
+import numpy as np
+import pytest
+
+from oracle.dense_sim import fidelity
+from tests import _baseline
+
+pytestmark = pytest.mark.gpu
+
+SV_TOL = 1e-5          # relative to sigma_max of the application, and per kept value >= 1e-3 sigma_max
+NORM_RTOL = 1e-4
+SAMPLED_FID_TOL = 1e-5
+AMP_REL_RMS = 1e-2
+
+
+def _triples(ops, chi):
+    return [(op.tensor, op.indices, {"maxsvals": chi, "keep_left_canonical": op.keep_left_canonical}) for op in ops]
+
+
+def _check_sigma(name, svals_per_app, base):
+    worst_max = worst_rel = 0.0
+    for t, (got, k, ref) in enumerate(zip(svals_per_app, base.k, base.svals)):
+        e_max, e_rel = _baseline.sigma_errors(got, k, ref)
+        worst_max, worst_rel = max(worst_max, e_max), max(worst_rel, e_rel)
+    print(f"{name}: worst singular-value error {worst_max:.2e} sigma_max, {worst_rel:.2e} per kept value "
+          f"over {len(base.svals)} applications")
+    assert worst_max <= SV_TOL, (name, worst_max)
+    assert worst_rel <= SV_TOL, (name, worst_rel)
+
+
+def _check_amplitudes(name, amps, norm, base):
+    ref = base.amp_values
+    rms = np.sqrt(np.mean(np.abs(ref) ** 2))
+    err = np.abs(amps - ref).max()
+    fid = _baseline.sampled_fidelity(amps, ref)
+    print(f"{name}: norm {norm:.6e} (ref {base.norm:.6e}), sampled infidelity {1 - fid:.2e}, "
+          f"max amplitude error {err / rms:.2e} rms")
+    assert abs(norm - base.norm) <= NORM_RTOL * base.norm
+    assert np.abs(amps - ref).max() <= 1e-4                       # the north star's absolute bound (weak here)
+    assert fid >= 1 - SAMPLED_FID_TOL
+    assert err <= AMP_REL_RMS * rms
+
+
+def test_config3_members_as_one_batch():
+    import mpsim_b200 as mp
+    from mpsim_b200 import circuits
+    members = (0, 511)
+    bases = [_baseline.Baseline(f"config3_member{m}") for m in members]
+    n, chi = bases[0].n, bases[0].chi
+    structure = circuits.brickwork(n, 20, seed=0)
+    batch = mp.MPSBatch(len(members), n)
+    cp = batch.compile(structure, record_svals=True, maxsvals=chi)
+    gates = np.stack([circuits.batch_member_gates(len(structure), m) for m in members], axis=1)
+    batch.stage_gates(cp, gates)
+    batch.run(cp)
+    assert (batch.status(cp)[..., 0] == 0).all()
+    sv = batch.singular_values(cp)
+    norms = batch.norms()
+    for b, base in enumerate(bases):
+        assert batch.bond_dimensions() == base.bond_dimensions
+        assert [a.k for a in cp.plan.apps2] == base.k
+        _check_sigma(base.name, [sv[t, b] for t in range(len(base.k))], base)
+        amps = batch.amplitudes(base.amp_bits)[b]
+        _check_amplitudes(base.name, amps, float(norms[b]), base)
+
+
+def test_snake_swap_network_block_jacobi():
+    import mpsim_b200 as mp
+    base = _baseline.Baseline("snake_4x4_chi96")
+    assert base.min_kept_over_max > 1e-6                          # full rank: the reference is well defined here
+    assert max(2 * max(c[0], c[2]) for c in base.app_chi) > 128   # reaches the block-Jacobi path
+    mps = mp.MPS(base.n)
+    mps.record_singular_values(True)
+    mps._execute(_triples(base.ops, base.chi))
+    assert (mps.last_status()[:, 0] == 0).all()
+    got = mps.last_singular_values()
+    assert [s["k"] for s in got] == base.k and [s["index"] for s in got] == base.app_index
+    assert mps.bond_dimensions() == base.bond_dimensions
+    _check_sigma(base.name, [s["svals"] for s in got], base)
+    _check_amplitudes(base.name, mps.amplitudes(base.amp_bits), mps.norm(), base)
+    wf = mps.wavefunction()
+    np.testing.assert_allclose(wf, base.wavefunction, atol=1e-4)
+    assert fidelity(wf, base.wavefunction.astype(np.complex128)) >= 1 - 1e-5
+
+
+def test_snake_norm_bookkeeping():
+    """mpsim/core.py:1160-1161: the norm after every adjacent application (SWAPs of the swap networks
+    included, the routed gate's entry after its swap-back), against the reference's own ``_norms``."""
+    import mpsim_b200 as mp
+    base = _baseline.Baseline("snake_4x4_chi96")
+    mps = mp.MPS(base.n, track_norms=True)
+    for op in base.ops:
+        mps.apply_two_qudit_gate(mp.Node(op.tensor), *op.indices, maxsvals=base.chi,
+                                 keep_left_canonical=op.keep_left_canonical)
+    assert len(mps._norms) == len(base.norms_after)
+    np.testing.assert_allclose(mps._norms, base.norms_after, rtol=1e-4)
+
+
+@pytest.mark.skipif(not _baseline.available("config2_full"), reason="fixture not generated")
+def test_config2_full_vs_oracle():
+    import mpsim_b200 as mp
+    base = _baseline.Baseline("config2_full")
+    mps = mp.MPS(base.n)
+    mps.record_singular_values(True)
+    mps._execute(_triples(base.ops, base.chi))
+    assert (mps.last_status()[:, 0] == 0).all()
+    got = mps.last_singular_values()
+    assert [s["k"] for s in got] == base.k
+    assert mps.bond_dimensions() == base.bond_dimensions
+    _check_sigma(base.name, [s["svals"] for s in got], base)
+    _check_amplitudes(base.name, mps.amplitudes(base.amp_bits), mps.norm(), base)
