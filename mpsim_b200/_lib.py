@@ -106,6 +106,7 @@ def to_device_bytes(arr: np.ndarray, device):
     return host.to(device, non_blocking=False)
 
 
-def stream_ptr() -> int:
+def stream_ptr(device=None) -> int:
+    """Raw handle of torch's current stream on ``device`` (default: the current device)."""
     import torch
-    return torch.cuda.current_stream().cuda_stream
+    return torch.cuda.current_stream(device).cuda_stream

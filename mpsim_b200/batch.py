@@ -73,15 +73,18 @@ class MPSBatch:
         return self._chain.norms()
 
     def norms(self) -> np.ndarray:
+        self._chain.check_status()
         return self._chain.norms().cpu().numpy()
 
     def amplitudes_device(self, bitstrings):
         return self._chain.amplitudes(bitstrings)
 
     def amplitudes(self, bitstrings) -> np.ndarray:
+        self._chain.check_status()
         return self._chain.amplitudes(bitstrings).cpu().numpy()
 
     def wavefunction(self, member: int) -> np.ndarray:
+        self._chain.check_status()
         return self._chain.wavefunction(int(member)).cpu().numpy()
 
     def renormalize(self, to_norm: float = 1.0) -> None:

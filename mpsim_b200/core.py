@@ -206,10 +206,16 @@ class MPS:
         """Device view of site ``index`` as a torch tensor [chi_left][d][chi_right]."""
         return self._chain.site_view(range(self._nqudits)[index])
 
+    def _device_guard(self):
+        """Context with the chain's device current (helpers outside DeviceChain take the current stream)."""
+        import torch
+        return torch.cuda.device(self._chain.device)
+
     # ------------------------------------------------------------------ contractions
     def wavefunction(self) -> np.ndarray:                            # core.py:483-500
         if not self.is_valid():
             raise ValueError("MPS is not valid.")
+        self._chain.check_status()
         return self._chain.wavefunction(0).cpu().numpy()
 
     def wavefunction_device(self):
@@ -217,6 +223,7 @@ class MPS:
 
     def amplitudes(self, bitstrings) -> np.ndarray:
         """<bits|psi> for selected basis states (the only option once d**n is out of reach)."""
+        self._chain.check_status()
         return self._chain.amplitudes(bitstrings)[0].cpu().numpy()
 
     def dagger(self) -> None:                                        # core.py:502-505
@@ -233,6 +240,7 @@ class MPS:
             raise ValueError("MPS is invalid.")
         if not other.is_valid():
             raise ValueError("Other MPS is invalid.")
+        self._chain.check_status()
         return complex(self._chain.inner_products(other._chain)[0].item())
 
     def norm(self) -> float:                                         # core.py:563-565
@@ -250,15 +258,18 @@ class MPS:
 
     def reduced_density_matrix(self, node_indices: Union[int, Sequence[int]]) -> np.ndarray:   # core.py:596-652
         from mpsim_b200 import observables
-        return observables.reduced_density_matrix(self, node_indices)
+        with self._device_guard():
+            return observables.reduced_density_matrix(self, node_indices)
 
     def sample(self, nsamples: int, as_hist: bool = False, as_string: bool = False) -> Any:      # core.py:684-721
         from mpsim_b200 import observables
-        return observables.sample(self, nsamples, as_hist, as_string)
+        with self._device_guard():
+            return observables.sample(self, nsamples, as_hist, as_string)
 
     def expectation(self, observable: MPSOperation) -> float:        # core.py:723-751
         from mpsim_b200 import observables
-        return observables.expectation(self, observable)
+        with self._device_guard():
+            return observables.expectation(self, observable)
 
     # ------------------------------------------------------------------ gate application
     def _execute(self, ops: Sequence[Tuple[np.ndarray, Tuple[int, ...], Dict[str, Any]]]) -> None:

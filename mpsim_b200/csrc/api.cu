@@ -4,6 +4,9 @@
 #include <string.h>
 #include <string>
 #include <vector>
+#include <mutex>
+#include <map>
+#include <utility>
 
 int launch_gate1(const mpsb_gate1_desc* descs, int ndesc, int nbatch, int d, int max_site_elems, cudaStream_t st);
 int launch_scale(const mpsb_site_ref* sites, int nsites, int nbatch, int d, const float* factors,
@@ -18,6 +21,34 @@ void mpsb_set_error(const char* fmt, ...) {
     va_start(ap, fmt);
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
+}
+
+// Developer switches (MPSB_* environment variables; not part of the ABI): each is read ONCE, at its
+// first use, and cached -- no getenv on the call path.  MPSB_DEV_REREAD_ENV=1 (itself read once)
+// turns the cache off for tests and A/B scripts that flip a switch between calls.
+const char* mpsb_env(const char* name) {
+    static const bool reread = [] { const char* e = getenv("MPSB_DEV_REREAD_ENV"); return e && atoi(e) != 0; }();
+    if (reread) return getenv(name);
+    static std::mutex mu;
+    static std::map<std::string, std::pair<bool, std::string>> cache;
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(name);
+    if (it == cache.end()) {
+        const char* e = getenv(name);
+        it = cache.emplace(name, std::make_pair(e != nullptr, std::string(e ? e : ""))).first;
+    }
+    return it->second.first ? it->second.second.c_str() : nullptr;
+}
+
+std::recursive_mutex& mpsb_lib_mutex() {
+    static std::recursive_mutex mu;
+    return mu;
+}
+
+int mpsb_current_device(int* dev) {
+    MPSB_CUDA(cudaGetDevice(dev));
+    MPSB_ARG(*dev >= 0 && *dev < MPSB_MAX_DEVICES, "device ordinal %d outside [0, %d)", *dev, MPSB_MAX_DEVICES);
+    return 0;
 }
 
 namespace {
@@ -58,7 +89,7 @@ struct Gate2Plan {
 // theta runs on the tensor cores (tc_gemm.cu) for qubits once the tile is reasonably filled;
 // MPSB_THETA_TC=0/1 forces the choice (debugging / A-B timing)
 bool theta_uses_tc(int d, int chiL, int chiM, int chiR) {
-    if (const char* e = getenv("MPSB_THETA_TC")) return atoi(e) != 0 && d == 2;
+    if (const char* e = mpsb_env("MPSB_THETA_TC")) return atoi(e) != 0 && d == 2;
     return d == 2 && chiL >= 32 && chiR >= 32 && chiM >= 16;
 }
 
@@ -69,7 +100,7 @@ Gate2Plan plan_gate2(int d, int chiL, int chiR, int lc) {
     p.L = lc ? p.n : p.m;
     p.small = p.m <= MPSB_MAX_SMALL_DIM && p.n <= MPSB_MAX_SMALL_DIM;
     p.x_elems = p.small ? (size_t)p.m * p.n : (size_t)svd_large_padded_rows(p.nv) * p.L;
-    p.extra_elems = p.small ? svd_small_global_z_elems(p.nv, p.L) : svd_large_workspace_elems(p.nv, p.L);
+    p.extra_elems = p.small ? (size_t)0 : svd_large_workspace_elems(p.nv, p.L);
     p.job_elems = align_up(p.x_elems, 16) + align_up(p.extra_elems, 16);
     return p;
 }
@@ -156,11 +187,18 @@ size_t mpsb_gate2_layer_workspace_bytes(const mpsb_gate2_group* g, int ngroups, 
     return tot;
 }
 
-// library-owned streams of mpsb_apply_gate2_layer (created once; never destroyed)
+// library-owned streams of mpsb_apply_gate2_layer: one pool per device ordinal, created on first use
+// under the library mutex, never destroyed.  Calls that use library-owned state (this pool, the pinned
+// read-back slots of svd_large.cu) serialise on that mutex: ctypes drops the GIL, so two host threads
+// may be inside the library at once.
 static const int kPoolStreams = 8;
-static cudaStream_t g_pool[kPoolStreams];
-static cudaEvent_t g_fork = nullptr, g_join[kPoolStreams];
-static bool g_pool_ready = false;
+struct StreamPool {
+    cudaStream_t s[kPoolStreams];
+    cudaEvent_t fork = nullptr, join[kPoolStreams];
+    bool ready = false;
+};
+static StreamPool g_pools[MPSB_MAX_DEVICES];
+
 
 int mpsb_apply_gate2_layer(const mpsb_gate2_group* groups, int ngroups, int nbatch, int d,
                            void* workspace, size_t workspace_bytes, void* stream) {
@@ -170,14 +208,21 @@ int mpsb_apply_gate2_layer(const mpsb_gate2_group* groups, int ngroups, int nbat
     if (ngroups == 0 || nbatch == 0) return 0;
     MPSB_ARG(workspace_bytes >= mpsb_gate2_layer_workspace_bytes(groups, ngroups, nbatch, d),
              "apply_gate2_layer: workspace too small");
-    if (!g_pool_ready) {
+    std::lock_guard<std::recursive_mutex> lock(mpsb_lib_mutex());
+    int dev = 0;
+    if (int rc = mpsb_current_device(&dev)) return rc;
+    StreamPool& pool = g_pools[dev];
+    if (!pool.ready) {
         for (int i = 0; i < kPoolStreams; ++i) {
-            MPSB_CUDA(cudaStreamCreateWithFlags(&g_pool[i], cudaStreamNonBlocking));
-            MPSB_CUDA(cudaEventCreateWithFlags(&g_join[i], cudaEventDisableTiming));
+            MPSB_CUDA(cudaStreamCreateWithFlags(&pool.s[i], cudaStreamNonBlocking));
+            MPSB_CUDA(cudaEventCreateWithFlags(&pool.join[i], cudaEventDisableTiming));
         }
-        MPSB_CUDA(cudaEventCreateWithFlags(&g_fork, cudaEventDisableTiming));
-        g_pool_ready = true;
+        MPSB_CUDA(cudaEventCreateWithFlags(&pool.fork, cudaEventDisableTiming));
+        pool.ready = true;
     }
+    cudaStream_t* g_pool = pool.s;
+    cudaEvent_t g_fork = pool.fork;
+    cudaEvent_t* g_join = pool.join;
     // heaviest group first: it stays on the caller's stream, the others go round the pool
     std::vector<int> order(ngroups);
     std::vector<double> cost(ngroups);
@@ -406,8 +451,8 @@ static size_t svd_x_elems(int m, int n) {
 size_t mpsb_svd_workspace_bytes(int njobs, int m, int n) {
     if (njobs <= 0 || m <= 0 || n <= 0) return 0;
     bool small = m <= MPSB_MAX_SMALL_DIM && n <= MPSB_MAX_SMALL_DIM;
-    size_t ex_a = small ? svd_small_global_z_elems(m, n) : svd_large_workspace_elems(m, n);
-    size_t ex_b = small ? svd_small_global_z_elems(n, m) : svd_large_workspace_elems(n, m);
+    size_t ex_a = small ? (size_t)0 : svd_large_workspace_elems(m, n);
+    size_t ex_b = small ? (size_t)0 : svd_large_workspace_elems(n, m);
     size_t ex = ex_a > ex_b ? ex_a : ex_b;
     return (align_up(svd_x_elems(m, n), 16) + align_up(ex, 16)) * sizeof(cf) * (size_t)njobs + 256;
 }

@@ -69,6 +69,16 @@ void mpsb_set_error(const char* fmt, ...);
         }                                                                            \
     } while (0)
 
+// library-owned state (stream pool, pinned read-back slots) is kept per device ordinal and guarded by
+// one mutex (api.cu)
+#define MPSB_MAX_DEVICES 16
+#ifdef __cplusplus
+#include <mutex>
+std::recursive_mutex& mpsb_lib_mutex();
+int mpsb_current_device(int* dev);
+const char* mpsb_env(const char* name);      // cached developer switches (api.cu)
+#endif
+
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // internal launchers (defined in the .cu files, used by api.cu)
@@ -84,7 +94,6 @@ int launch_theta_tc(const mpsb_gate2_desc* descs, int ndesc, int nbatch, int chi
                     int transpose_out, cf* out, int64_t out_job_stride, float* work, cudaStream_t st);
 int launch_cgemm_tc(const cf* A, int64_t a_bs, const cf* B, int64_t b_bs, cf* C, int64_t c_ld, int64_t c_bs,
                     int M, int N, int K, int nbatch, float* work, cudaStream_t st);
-size_t svd_small_global_z_elems(int nv, int L);
 int launch_svd_small(const cf* X, int64_t x_job_stride, int njobs, int nv, int L, int k,
                      int left_canonical, const mpsb_gate2_desc* descs, int ndesc, int nbatch,
                      cf* left, int64_t left_stride, cf* right, int64_t right_stride,

@@ -952,7 +952,7 @@ struct PinSlot {
     size_t jobs_cap = 0;
     cudaEvent_t ev[MAX_CHECKS] = {nullptr, nullptr};
 };
-static PinSlot g_pin[PIN_SLOTS];
+static PinSlot g_pin[MPSB_MAX_DEVICES][PIN_SLOTS];      // guarded by mpsb_lib_mutex()
 
 struct LargeRun {
     LargeParams p;
@@ -995,7 +995,7 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
         const int ntile_all = (L + GK - 1) / GK;
         for (int ns = 4; ns > 1; ns >>= 1)
             if (ns <= ntile_all && (long long)njobs * lo.npairs * ns <= 148 && (size_t)lo.npairs * ns * P * P <= lo.z) { p.nsplit = ns; break; }
-        if (const char* e = getenv("MPSB_LARGE_NSPLIT")) {   // timing experiments only
+        if (const char* e = mpsb_env("MPSB_LARGE_NSPLIT")) {   // timing experiments only
             int ns = atoi(e);
             if (ns >= 1 && ns <= ntile_all && (size_t)lo.npairs * ns * P * P <= lo.z) p.nsplit = ns;
         }
@@ -1009,12 +1009,14 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
     if (floor_ > tol) tol = floor_;
     p.tol2 = tol * tol;
     float eta = ABS_ETA;
-    if (const char* e = getenv("MPSB_LARGE_ETA")) eta = (float)atof(e);          // experiments only
+    if (const char* e = mpsb_env("MPSB_LARGE_ETA")) eta = (float)atof(e);          // experiments only
     p.eta2 = eta * eta;
     p.clk = nullptr;
-    if (getenv("MPSB_LARGE_CLOCKS")) {                        // profiling only: leaks 64 bytes per call
-        MPSB_CUDA(cudaMalloc((void**)&p.clk, 8 * sizeof(long long)));
-        MPSB_CUDA(cudaMemset(p.clk, 0, 8 * sizeof(long long)));
+    if (mpsb_env("MPSB_LARGE_CLOCKS")) {                        // profiling only: one 64-byte buffer per process
+        static long long* clk_buf = nullptr;
+        if (!clk_buf) MPSB_CUDA(cudaMalloc((void**)&clk_buf, 8 * sizeof(long long)));
+        p.clk = clk_buf;
+        MPSB_CUDA(cudaMemsetAsync(p.clk, 0, 8 * sizeof(long long), st));
     }
     r.lo = lo; r.njobs = njobs; r.nv = nv; r.L = L; r.st = st;
     r.nrounds = lo.nb > 2 ? lo.nb - 1 : 1;
@@ -1027,28 +1029,30 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
     // Gram tile ring: two stages when several CTAs share an SM (they hide each other's loads), four
     // when the launch has fewer CTAs than SMs
     r.gram_stages = (long long)njobs * lo.npairs >= 2 * 148 ? 2 : GRAM_MAX_STAGES;     // (no measurable effect either way)
-    if (const char* e = getenv("MPSB_LARGE_STAGES")) r.gram_stages = atoi(e) >= 2 && atoi(e) <= GRAM_MAX_STAGES ? atoi(e) : r.gram_stages;
+    if (const char* e = mpsb_env("MPSB_LARGE_STAGES")) r.gram_stages = atoi(e) >= 2 && atoi(e) <= GRAM_MAX_STAGES ? atoi(e) : r.gram_stages;
     // 512 threads do not help a launch with fewer CTAs than SMs either (measured: a single 256 x 256
     // solve 9.4 ms against 8.9 ms): one pair's Gram is bound by the FFMA issue rate of ONE SM, and the
     // pass by its ~1 200-cycle dependent chain per rotation set (parameters 500, update 600)
     r.gram_threads = 256;
-    if (const char* e = getenv("MPSB_LARGE_GTHREADS")) r.gram_threads = atoi(e) == 512 ? 512 : 256;   // experiments only
+    if (const char* e = mpsb_env("MPSB_LARGE_GTHREADS")) r.gram_threads = atoi(e) == 512 ? 512 : 256;   // experiments only
     r.pdl = 1;
-    if (const char* e = getenv("MPSB_LARGE_NT")) r.nt_cta = atoi(e) > 0 ? atoi(e) : r.nt_cta;   // timing experiments only
-    if (const char* e = getenv("MPSB_LARGE_PDL")) r.pdl = atoi(e);
+    if (const char* e = mpsb_env("MPSB_LARGE_NT")) r.nt_cta = atoi(e) > 0 ? atoi(e) : r.nt_cta;   // timing experiments only
+    if (const char* e = mpsb_env("MPSB_LARGE_PDL")) r.pdl = atoi(e);
     // the tensor-core apply (bj_apply_tc_kernel) is persistent, one CTA per SM: taken when there are
     // at least two tiles per SM, otherwise the FFMA kernel (a single 256 x 256 matrix is 32 tiles)
     r.tc_apply = (long long)njobs * lo.npairs * (r.ntx + r.ntz) >= 2 * 148;
-    if (const char* e = getenv("MPSB_LARGE_TC_APPLY")) r.tc_apply = atoi(e) != 0;       // A/B timing
+    if (const char* e = mpsb_env("MPSB_LARGE_TC_APPLY")) r.tc_apply = atoi(e) != 0;       // A/B timing
     r.skip = 0; r.max_outer = MAX_OUTER;
-    if (const char* e = getenv("MPSB_LARGE_SKIP")) r.skip = atoi(e);
-    if (const char* e = getenv("MPSB_LARGE_SWEEPS")) r.max_outer = atoi(e);
+    if (const char* e = mpsb_env("MPSB_LARGE_SKIP")) r.skip = atoi(e);
+    if (const char* e = mpsb_env("MPSB_LARGE_SWEEPS")) r.max_outer = atoi(e);
     OutParams& o = r.o;
     o.descs = descs; o.nbatch = nbatch > 0 ? nbatch : 1;
     o.left = left; o.left_stride = left_stride; o.right = right; o.right_stride = right_stride;
     o.svals = svals; o.svals_stride = svals_stride; o.info = info; o.k = k; o.lc = left_canonical;
     // pinned read-back area of this slot (a slot is only ever written from one stream at a time)
-    PinSlot& pin = g_pin[pin_slot];
+    int dev = 0;
+    if (int rc = mpsb_current_device(&dev)) return rc;
+    PinSlot& pin = g_pin[dev][pin_slot];
     if (pin.jobs_cap < (size_t)njobs) {
         if (pin.host) { MPSB_CUDA(cudaDeviceSynchronize()); cudaFreeHost(pin.host); pin.host = nullptr; }
         pin.jobs_cap = (size_t)njobs > 4096 ? (size_t)njobs : 4096;
@@ -1057,7 +1061,8 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
     for (int i = 0; i < MAX_CHECKS; ++i)
         if (!pin.ev[i]) MPSB_CUDA(cudaEventCreateWithFlags(&pin.ev[i], cudaEventDisableTiming));
     r.pin = &pin;
-    static bool attrs = false;
+    static bool attrs_set[MPSB_MAX_DEVICES] = {};
+    bool& attrs = attrs_set[dev];
     if (!attrs) {
         MPSB_CUDA(cudaFuncSetAttribute(bj_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, APPLY_SMEM));
         MPSB_CUDA(cudaFuncSetAttribute(bj_apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
@@ -1202,6 +1207,7 @@ int launch_svd_large(cf* X, int64_t x_job_stride, int njobs, int nv, int L, int 
                      cudaStream_t st) {
     (void)ndesc;
     if (njobs <= 0) return 0;
+    std::lock_guard<std::recursive_mutex> lock(mpsb_lib_mutex());
     LargeRun r;
     int rc = large_begin(r, X, x_job_stride, njobs, nv, L, k, left_canonical, descs, nbatch, left, left_stride,
                          right, right_stride, svals, svals_stride, info, work, st, PIN_SLOTS - 1);
@@ -1215,6 +1221,7 @@ int launch_svd_large(cf* X, int64_t x_job_stride, int njobs, int nv, int L, int 
 // begin all, keep every stream fed by polling, finish each as soon as it has converged.
 
 int launch_svd_large_multi(const LargeMultiJob* jobs, int n) {
+    std::lock_guard<std::recursive_mutex> lock(mpsb_lib_mutex());
     std::vector<LargeRun> runs(n);
     std::vector<char> finished(n, 0);
     for (int i = 0; i < n; ++i) {

@@ -40,10 +40,15 @@ constexpr int XCH = 32;          // staging chunk of X: columns in step 4, rows 
 constexpr int XS_ELEMS = 128 * (XCH + 1);   // >= XCH * (128 + 4)
 constexpr float BIG2 = 1e-4f * 1e-4f;       // a sweep without a rotation above this is the last
 
-// phase boundaries of CTA 0 (clock64), read back by mpsb_debug_phase_clocks: a profiling aid
+// Profiling build only (MPSB_NVCC_EXTRA=-DMPSB_PROFILE, scripts/prof_svd.py): phase boundaries of
+// CTA 0 (clock64), read back through mpsb_debug_phase_clocks.  The release library carries neither
+// the marks nor the export.
+#ifdef MPSB_PROFILE
 __device__ long long g_phase_clk[32];
-__device__ int g_dbg_flags;      // timing experiments only (set through mpsb_debug_set_flags)
 #define PHASE_MARK(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) g_phase_clk[i] = clock64(); } while (0)
+#else
+#define PHASE_MARK(i) do { } while (0)
+#endif
 
 struct SvdSmallParams {
     const cf* X; int64_t x_stride;
@@ -300,19 +305,13 @@ __device__ __noinline__ void householder(cf* A, int LS, int nrows, int ncols, in
     __syncthreads();
     cf my_alpha = cf_make(0.f, 0.f), my_v0 = cf_make(0.f, 0.f);
     bool my_reflect = false;
-    const int dbg = g_dbg_flags;
     for (int j = 0; j < nsteps; ++j) {
         const int cur = j & 1, nxt = cur ^ 1;
         const cf* vbl = vbuf + cur * VB;
-        // step-10 timeline of the threads that publish column 11 (profiling aid, CTA 0, MODE 0)
-        const bool probe = MODE == 0 && j == 10 && blockIdx.x == 0 && mine && col == 11 && sub == 0;
-        if (probe) g_phase_clk[16] = clock64();
         float tail2 = 0.f;
-        if (!(dbg & 4)) {
 #pragma unroll
-            for (int m = 0; m < 4; ++m) tail2 += cf_abs2(vbl[lane + 32 * m]);
-            tail2 = warp_sum(tail2);
-        } else tail2 = 1.0f;
+        for (int m = 0; m < 4; ++m) tail2 += cf_abs2(vbl[lane + 32 * m]);
+        tail2 = warp_sum(tail2);
         cf x0 = cf_make(scal[cur * 4 + 0], scal[cur * 4 + 1]);
         float ax0sq = cf_abs2(x0);
         // |x0|^2 below ~1e-30 is a denormal-range number with few significant bits: the
@@ -324,25 +323,21 @@ __device__ __noinline__ void householder(cf* A, int LS, int nrows, int ncols, in
         const bool reflect = tail2 > 0.f && tail2 + ax0sq > 1e-30f;
         cf v0 = cf_make(0.f, 0.f), alpha = cf_make(0.f, 0.f);
         float tau = 0.f;
-        if (reflect && !(dbg & 8)) {
+        if (reflect) {
             float ax0 = sqrtf(ax0sq);
             float normx = sqrtf(tail2 + ax0sq);
             cf ph = ax0 > 0.f ? cf_scale(1.0f / ax0, x0) : cf_make(1.f, 0.f);
             alpha = cf_scale(-normx, ph);
             v0 = cf_sub(x0, alpha);
             tau = 1.0f / (normx * (normx + ax0));
-        } else if (reflect) { v0 = x0; tau = 0.5f; }
+        }
         if (MODE == 1 && tid == 0) { tau_arr[j] = tau; v0_arr[j] = v0; }
         if (mine && col == j) { my_alpha = alpha; my_v0 = v0; my_reflect = reflect; }
-        if (probe) g_phase_clk[17] = clock64();
         if (mine && col > j) {
-            if (reflect && !(dbg & 1)) reflect_column(vbl + sub, j, v0, tau);
-            if (probe) g_phase_clk[18] = clock64();
-            if (col == j + 1 && j + 1 < nsteps && !(dbg & 2)) publish(j + 1, vbuf + nxt * VB + sub, scal + nxt * 4);
+            if (reflect) reflect_column(vbl + sub, j, v0, tau);
+            if (col == j + 1 && j + 1 < nsteps) publish(j + 1, vbuf + nxt * VB + sub, scal + nxt * 4);
         }
-        if (probe) g_phase_clk[19] = clock64();
         __syncthreads();
-        if (probe) g_phase_clk[20] = clock64();
     }
     if (MODE == 1) {
         // backward: Q <- H_j Q for j = k-1 .. 0, in the same registers
@@ -782,16 +777,11 @@ Layout make_layout(int nv, int L) {
 
 }  // namespace
 
-extern "C" int mpsb_debug_set_flags(int flags) {
-    return (int)cudaMemcpyToSymbol(g_dbg_flags, &flags, sizeof(int));
+#ifdef MPSB_PROFILE
+extern "C" int mpsb_debug_phase_clocks(long long* out32) {
+    return (int)cudaMemcpyFromSymbol(out32, g_phase_clk, sizeof(long long) * 32);
 }
-
-extern "C" int mpsb_debug_phase_clocks(long long* out16) {
-    return (int)cudaMemcpyFromSymbol(out16, g_phase_clk, sizeof(long long) * 32);
-}
-
-// (the Z spill of the first implementation is gone: nothing is needed in global memory)
-size_t svd_small_global_z_elems(int nv, int L) { (void)nv; (void)L; return 0; }
+#endif
 
 int launch_svd_small(const cf* X, int64_t x_job_stride, int njobs, int nv, int L, int k,
                      int left_canonical, const mpsb_gate2_desc* descs, int ndesc, int nbatch,
@@ -817,9 +807,9 @@ int launch_svd_small(const cf* X, int64_t x_job_stride, int njobs, int nv, int L
     P.do_qr = 1;
     P.use_ns = 1;
     // debugging knobs (not part of the ABI)
-    if (const char* e = getenv("MPSB_SVD_MAX_SWEEPS")) P.max_sweeps = atoi(e);
-    if (const char* e = getenv("MPSB_SVD_NO_QR")) P.do_qr = atoi(e) ? 0 : 1;
-    if (const char* e = getenv("MPSB_SVD_NO_NS")) P.use_ns = atoi(e) ? 0 : 1;
+    if (const char* e = mpsb_env("MPSB_SVD_MAX_SWEEPS")) P.max_sweeps = atoi(e);
+    if (const char* e = mpsb_env("MPSB_SVD_NO_QR")) P.do_qr = atoi(e) ? 0 : 1;
+    if (const char* e = mpsb_env("MPSB_SVD_NO_NS")) P.use_ns = atoi(e) ? 0 : 1;
     MPSB_CUDA(cudaFuncSetAttribute(svd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lo.smem));
     svd_small_kernel<<<njobs, ST, lo.smem, st>>>(P);
     MPSB_LAUNCH_CHECK("svd_small_kernel");

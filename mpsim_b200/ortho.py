@@ -29,6 +29,12 @@ def _device_svd(mat, left_canonical: bool):
     _lib.check(lib.mpsb_svd(mat.data_ptr(), 1, m, n, k, 1 if left_canonical else 0, left.data_ptr(),
                             right.data_ptr(), sv.data_ptr(), info.data_ptr(), ws.data_ptr(), ws.numel(),
                             _lib.stream_ptr()), "mpsb_svd")
+    status = int(info[0].item())
+    if status != 0:
+        import warnings
+        from mpsim_b200.store import SVDNotConverged
+        warnings.warn(f"mpsb_svd of a {m} x {n} site reached its sweep limit while still rotating",
+                      SVDNotConverged, stacklevel=3)
     return left, right, sv
 
 
@@ -46,9 +52,20 @@ def _device_matmul(a, b):
     return c
 
 
+#: numerically zero singular values of a rank-deficient site come out of the fp32 Jacobi SVD at
+#: ~eps32 * sigma_max * sqrt(min(m, n)); the reference's complex128 SVD returns them at ~1e-16 and
+#: drops them with its 1e-8 * norm cut.  The cut is clamped to this floor so that the bond dimension
+#: after a non-unitary gate matches the reference's.
+_FP32_ZERO_FLOOR = 8.0 * float(np.finfo(np.float32).eps)
+
+
 def _keep_count(svals: np.ndarray, max_truncation_err: float) -> int:
-    """tensornetwork 0.2.1 svd_decomposition: number of values whose tail norm exceeds the bound."""
-    trunc_errs = np.sqrt(np.cumsum(np.square(svals[::-1].astype(np.float64))))
+    """tensornetwork 0.2.1 svd_decomposition: number of values whose tail norm exceeds the bound
+    (the bound clamped to the fp32 noise floor of the device SVD, see ``_FP32_ZERO_FLOOR``)."""
+    sv = svals.astype(np.float64)
+    if sv.size:
+        max_truncation_err = max(max_truncation_err, _FP32_ZERO_FLOOR * sv.max() * np.sqrt(sv.size))
+    trunc_errs = np.sqrt(np.cumsum(np.square(sv[::-1])))
     return int(np.count_nonzero(trunc_errs > max_truncation_err))
 
 
@@ -57,6 +74,11 @@ def orthonormalize_right_edge_of(mps, node_index: int, threshold: float = 1e-8) 
     if not 0 <= node_index < mps._nqudits - 1:
         raise ValueError("Invalid edge index.")
     chain = mps._chain
+    with mps._device_guard():
+        _right(mps, chain, node_index, threshold)
+
+
+def _right(mps, chain, node_index: int, threshold: float) -> None:
     a = chain.site_view(node_index).clone()
     cl, d, cr = a.shape
     err = threshold * mps.norm()
@@ -73,6 +95,11 @@ def orthonormalize_left_edge_of(mps, node_index: int, threshold: float = 1e-8) -
     if not 0 < node_index <= mps._nqudits - 1:
         raise ValueError("Invalid edge index.")
     chain = mps._chain
+    with mps._device_guard():
+        _left(mps, chain, node_index, threshold)
+
+
+def _left(mps, chain, node_index: int, threshold: float) -> None:
     a = chain.site_view(node_index).clone()
     cl, d, cr = a.shape
     err = threshold * mps.norm()

@@ -30,10 +30,30 @@ def _torch():
     return torch
 
 
+def _on_device(fn):
+    """Run a DeviceChain method with the chain's device current: the C-ABI launches on the stream it
+    is handed, and ``_lib.stream_ptr`` / the library's per-device stream pool follow the current device."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        with _torch().cuda.device(self.device):
+            return fn(self, *args, **kwargs)
+    return wrapper
+
+
+class SVDNotConverged(RuntimeWarning):
+    """A Jacobi solve hit its sweep limit while still rotating (status word 1 of the C-ABI's ``info``):
+    the factors are still an exact orthogonal projection of theta, but the kept subspace and singular
+    values may differ from the reference's LAPACK SVD by more than the parity bound."""
+
+
 class CompiledPlan:
     """A plan bound to a chain's buffers: device descriptor tables + the launch list."""
 
     def __init__(self) -> None:
+        self.layout_gen = -1
+        self.owner = None
         self.launches: List[Tuple] = []
         self.desc1 = None
         self.desc2 = None
@@ -63,9 +83,12 @@ class DeviceChain:
         if caps is not None:
             self.caps = [max(1, int(c)) for c in caps]
             self.caps[0] = self.caps[-1] = 1
-        self._alloc(self.caps)
-        self._workspace = None
-        self.reset()
+        self._layout_gen = 0
+        self._status_flags = []          # device scalars: max SVD status of every run() since the last check
+        with torch.cuda.device(self.device):
+            self._alloc(self.caps)
+            self._workspace = None
+            self.reset()
 
     # ------------------------------------------------------------------ layout
     def _offsets(self, caps: Sequence[int]) -> Tuple[List[int], int]:
@@ -81,7 +104,9 @@ class DeviceChain:
         self.caps = list(caps)
         self.offs, self.total = self._offsets(self.caps)
         self.slab = torch.zeros((self.B, self.total), dtype=torch.complex64, device=self.device)
+        self._layout_gen += 1
 
+    @_on_device
     def ensure_caps(self, caps: Sequence[int]) -> None:
         """Grow bond capacities (re-lays the slab out and copies the live tensors)."""
         new = [max(a, b) for a, b in zip(self.caps, caps)]
@@ -94,6 +119,7 @@ class DeviceChain:
             if ne:
                 self.slab[:, self.offs[i]:self.offs[i] + ne] = old_slab[:, old_offs[i]:old_offs[i] + ne]
 
+    @_on_device
     def reset(self) -> None:
         """|0...0> on every batch member (``mpsim/core.py:190-218``)."""
         self.bonds = [1] * (self.n + 1)
@@ -111,6 +137,7 @@ class DeviceChain:
         ne = self.site_elems(i)
         return self.slab[b, self.offs[i]:self.offs[i] + ne].view(self.bonds[i], self.d, self.bonds[i + 1])
 
+    @_on_device
     def set_site(self, i: int, tensor, b: Optional[int] = None) -> None:
         """Overwrite site i (all batch members, or one) with a [chiL][d][chiR] tensor."""
         torch = _torch()
@@ -134,6 +161,8 @@ class DeviceChain:
         new.offs, new.total = list(self.offs), self.total
         new.slab = self.slab.clone()
         new._workspace = None
+        new._layout_gen = 0
+        new._status_flags = list(self._status_flags)
         return new
 
     def _site_refs(self) -> np.ndarray:
@@ -151,6 +180,7 @@ class DeviceChain:
         return self._workspace
 
     # ------------------------------------------------------------------ plan compilation
+    @_on_device
     def compile(self, plan: Plan, per_batch_gates: bool = False, record_svals: bool = False) -> CompiledPlan:
         """Bind ``plan`` (made against the chain's current bonds) to this chain's buffers."""
         torch = _torch()
@@ -242,19 +272,27 @@ class DeviceChain:
         cp.launches = launches
         cp.workspace_bytes = int(ws_need)
         cp.slab_ptr = self.slab.data_ptr()
+        cp.layout_gen = self._layout_gen
+        cp.owner = self
         # stage the gates of the plan itself (callers may overwrite cp.gates_host and re-upload)
         tab = plan.gate_table(width)
         if ng:
             cp.gates_host[:ng] = torch.from_numpy(tab).unsqueeze(1)
         return cp
 
+    @_on_device
     def upload_gates(self, cp: CompiledPlan) -> None:
         cp.gates.copy_(cp.gates_host, non_blocking=True)
 
+    @_on_device
     def run(self, cp: CompiledPlan, upload: bool = True) -> None:
         """Launch a compiled plan on the current stream (asynchronous)."""
         lib = _lib.load(require_device=True)
-        assert cp.slab_ptr == self.slab.data_ptr(), "chain buffers moved since the plan was compiled"
+        if cp.owner is not self or cp.layout_gen != self._layout_gen or cp.slab_ptr != self.slab.data_ptr():
+            raise RuntimeError("chain buffers were re-laid out since the plan was compiled: compile it again")
+        if cp.plan.bonds_in != self.bonds:
+            raise RuntimeError("the chain's bond dimensions differ from the ones the plan was compiled for "
+                               "(run the plan on the state it was planned against, e.g. after reset())")
         if upload:
             self.upload_gates(cp)
         ws = self.workspace(cp.workspace_bytes)
@@ -277,8 +315,28 @@ class DeviceChain:
                            "mpsb_apply_gate2")
         cp.n_launch_calls = len(cp.launches)
         self.bonds = list(cp.bonds_out)
+        if cp.plan.apps2:
+            self._status_flags.append(cp.info[: len(cp.plan.apps2) * B, 0].max())
+            if len(self._status_flags) >= 256:
+                self._status_flags = [_torch().stack(self._status_flags).max()]
+
+    def check_status(self) -> int:
+        """Largest SVD status word of every run() since the last call (0 = all converged); warns
+        (``SVDNotConverged``) when a solve hit its sweep limit.  Called by the host-returning paths
+        (norm, wavefunction, amplitudes), which synchronise anyway."""
+        if not self._status_flags:
+            return 0
+        worst = int(_torch().stack(self._status_flags).max().item())
+        self._status_flags = []
+        if worst != 0:
+            import warnings
+            warnings.warn("a truncated SVD reached its sweep limit while still rotating (status "
+                          f"{worst}); singular values of that application may be off by more than 1e-5",
+                          SVDNotConverged, stacklevel=3)
+        return worst
 
     # ------------------------------------------------------------------ whole-chain contractions
+    @_on_device
     def inner_products(self, other: Optional["DeviceChain"] = None):
         """<self|other> per batch member (sum self * conj(other), ``mpsim/core.py:543-561``):
         device complex64 [B]."""
@@ -300,6 +358,7 @@ class DeviceChain:
         torch = _torch()
         return torch.sqrt(torch.clamp(self.inner_products().real, min=0.0))
 
+    @_on_device
     def scale(self, factors) -> None:
         """site <- factors[b] * site for all sites (``mpsim/core.py:590-594``)."""
         torch = _torch()
@@ -314,6 +373,7 @@ class DeviceChain:
             _lib.check(lib.mpsb_scale_sites(refs.data_ptr() + s0 * _lib.SITE_REF.itemsize, c, self.B, self.d,
                                             f.data_ptr(), max(max_elems, 1), _lib.stream_ptr()), "mpsb_scale_sites")
 
+    @_on_device
     def wavefunction(self, b: int = 0):
         """device complex64 [d**n], big-endian (``mpsim/core.py:483-500``)."""
         torch = _torch()
@@ -326,6 +386,7 @@ class DeviceChain:
                                          ws.numel(), _lib.stream_ptr()), "mpsb_wavefunction")
         return out
 
+    @_on_device
     def amplitudes(self, bitstrings):
         """device complex64 [B][nbits]: <bits|psi_b> for each row of ``bitstrings`` (nbits x n)."""
         torch = _torch()

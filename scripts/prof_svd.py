@@ -10,8 +10,6 @@ m = int(sys.argv[2]) if len(sys.argv) > 2 else 128
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 2
 lib = _lib.load(require_device=True)
 import os
-if os.environ.get('DBG'):
-    lib.mpsb_debug_set_flags(int(os.environ['DBG']))
 rng = np.random.default_rng(0)
 a = rng.standard_normal((njobs, m, m)) + 1j * rng.standard_normal((njobs, m, m))
 u, s, vh = np.linalg.svd(a)
@@ -38,5 +36,4 @@ clk = (ctypes.c_longlong * 32)()
 if hasattr(lib, "mpsb_debug_phase_clocks") and lib.mpsb_debug_phase_clocks(clk) == 0:
     names = ["load", "qr1", "jacobi", "sort", "W=XV", "qr2+formQ", "P=QhX", "write"]
     c = list(clk)
-    print("householder step 10 (publisher thread): scalars %d reflect %d publish %d barrier %d" % (c[17] - c[16], c[18] - c[17], c[19] - c[18], c[20] - c[19]))
     print("phase cycles (CTA 0):", {n: c[i + 1] - c[i] for i, n in enumerate(names)}, "total", c[8] - c[0])

@@ -25,3 +25,9 @@ def pytest_collection_modifyitems(config, items):
     for item in items:
         if "gpu" in item.keywords:
             item.add_marker(skip)
+
+
+# The library caches its developer switches (MPSB_* environment variables) at first use; tests that
+# force a kernel choice per call (monkeypatch.setenv) need them re-read.  Must be set before the
+# shared library is loaded.
+os.environ.setdefault("MPSB_DEV_REREAD_ENV", "1")
