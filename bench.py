@@ -64,11 +64,10 @@ def workload_config(args, n_gpus):
 # synthetic inputs
 # ------------------------------------------------------------------------------------------------
 def haar_gates(count, rng):
-    """count Haar-random 4x4 unitaries (Mezzadri; mpsim/gates.py:269-286), vectorised."""
-    z = (rng.standard_normal((count, 4, 4)) + 1j * rng.standard_normal((count, 4, 4))) / np.sqrt(2)
-    q, r = np.linalg.qr(z)
-    dg = np.diagonal(r, axis1=1, axis2=2)
-    return (q * (dg / np.abs(dg))[:, None, :]).astype(np.complex64)
+    """count Haar-random 4x4 unitaries (Mezzadri; mpsim/gates.py:269-286), vectorised: the workload's own
+    generator (mpsim_b200.circuits.haar_gate_stack), shared by the GPU arm, the CPU arms and the fixtures."""
+    from mpsim_b200 import circuits
+    return circuits.haar_gate_stack(count, rng)
 
 
 def flops_svd_lapack(m, n):
@@ -149,7 +148,8 @@ def _oracle_one_circuit(payload):
         ctx = None
     from oracle.mps_oracle import OracleMPS
     from mpsim_b200 import circuits
-    ops = circuits.brickwork(nq, depth, seed)
+    # circuit `seed - 1000` of the batched workload: the very gate arrays the GPU arm stages for that member
+    ops = circuits.brickwork_member(nq, depth, seed - 1000)
     t0 = time.perf_counter()
     mps = OracleMPS(nq, dtype=np.complex128, track_norms=track)
     for op in ops:
@@ -512,7 +512,7 @@ def run_our_arm(args):
     # per-circuit Haar gates: circuit c of the global batch uses the stream seeded 1000 + c
     gates = np.empty((nops, B, 16), dtype=np.complex64)
     for b in range(B):
-        gates[:, b, :] = haar_gates(nops, np.random.default_rng(1000 + lo + b)).reshape(nops, 16)
+        gates[:, b, :] = circuits.batch_member_gates(nops, lo + b)        # stream seeded 1000 + member
     gates_pinned = torch.from_numpy(gates).pin_memory()
     norms_host = torch.empty(B, dtype=torch.float32).pin_memory()
     h2d = gates_pinned.numel() * 8

@@ -87,6 +87,12 @@ class MPSBatch:
         self._chain.check_status()
         return self._chain.wavefunction(int(member)).cpu().numpy()
 
+    def member(self, b: int):
+        """Member ``b`` as an ``MPS`` of its own (a copy of its site tensors)."""
+        from mpsim_b200.core import MPS
+        self._chain.check_status()
+        return MPS._from_chain(self._chain.member(b))
+
     def renormalize(self, to_norm: float = 1.0) -> None:
         """Per-member ``MPS.renormalize`` (``mpsim/core.py:567-594``); norms stay on the device."""
         import torch

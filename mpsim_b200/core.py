@@ -531,6 +531,19 @@ class MPS:
         new._last_bond_from_right = self._last_bond_from_right
         return new
 
+    @classmethod
+    def _from_chain(cls, chain, tensor_prefix: str = "q") -> "MPS":
+        """An MPS around an existing one-member ``DeviceChain`` (e.g. ``MPSBatch`` member views)."""
+        assert chain.B == 1
+        new = cls.__new__(cls)
+        new._nqudits, new._qudit_dimension, new._prefix = chain.n, chain.d, tensor_prefix
+        new._chain = chain
+        new._max_bond_dimensions = max_bond_dimensions(chain.n, chain.d)
+        new._track_norms, new._norms = False, []
+        new._last, new._record_svals = None, False
+        new._last_bond_from_right = chain.n >= 3
+        return new
+
     def __str__(self) -> str:
         return "----".join(self._prefix + str(i) for i in range(self._nqudits))
 

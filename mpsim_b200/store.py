@@ -165,6 +165,19 @@ class DeviceChain:
         new._status_flags = list(self._status_flags)
         return new
 
+    @_on_device
+    def member(self, b: int) -> "DeviceChain":
+        """Batch member ``b`` as a chain of its own (a copy: same layout, one slab row)."""
+        new = DeviceChain.__new__(DeviceChain)
+        new.n, new.d, new.B, new.device = self.n, self.d, 1, self.device
+        new.bonds, new.caps = list(self.bonds), list(self.caps)
+        new.offs, new.total = list(self.offs), self.total
+        new.slab = self.slab[int(b):int(b) + 1].clone()
+        new._workspace = None
+        new._layout_gen = 0
+        new._status_flags = []
+        return new
+
     def _site_refs(self) -> np.ndarray:
         refs = np.zeros(self.n, dtype=_lib.SITE_REF)
         for i in range(self.n):

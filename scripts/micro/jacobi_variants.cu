@@ -75,8 +75,10 @@ __device__ __forceinline__ float reduce4(const float (&g)[4], int lane) {
     return k;
 }
 
-template <int A0, int A1, int A2, int A3, int B0, int B1, int B2, int B3>
-__device__ __forceinline__ int sub_round_v0(cf (&y)[8][4], float (&a)[8], int lane, bool& big) {
+#define TICK(k) do { if (PROF) { const unsigned now_ = (unsigned)clock(); acc[k] += now_ - tlast; tlast = now_; } } while (0)
+
+template <bool PROF, int A0, int A1, int A2, int A3, int B0, int B1, int B2, int B3>
+__device__ __forceinline__ int sub_round_v0(cf (&y)[8][4], float (&a)[8], int lane, bool& big, unsigned (&acc)[8], unsigned& tlast) {
     constexpr int PA[4] = {A0, A1, A2, A3}, PB[4] = {B0, B1, B2, B3};
     float gr[4], gi[4];
 #pragma unroll
@@ -90,7 +92,11 @@ __device__ __forceinline__ int sub_round_v0(cf (&y)[8][4], float (&a)[8], int la
         }
         gr[i] = r; gi[i] = m;
     }
+    if (PROF) { asm volatile("" :: "f"(gr[0]), "f"(gr[1]), "f"(gr[2]), "f"(gr[3]), "f"(gi[0]), "f"(gi[1]), "f"(gi[2]), "f"(gi[3])); }
+    TICK(0);
     const float mgr = reduce4(gr, lane), mgi = reduce4(gi, lane);
+    if (PROF) { asm volatile("" :: "f"(mgr), "f"(mgi)); }
+    TICK(1);
     const int sel = lane >> 3;
     float ap = a[PA[0]], aq = a[PB[0]];
 #pragma unroll
@@ -100,6 +106,8 @@ __device__ __forceinline__ int sub_round_v0(cf (&y)[8][4], float (&a)[8], int la
     const bool dorot = (g2 > TOL2 * apq) && (g2 > 1e-30f);
     big = big || (dorot && g2 > BIG2 * apq);
     if (dorot) rot_params(ap, aq, mgr, mgi, g2, c, sr, si, tg);
+    if (PROF) { asm volatile("" :: "f"(c), "f"(sr), "f"(si), "f"(tg)); }
+    TICK(2);
     const unsigned bal = __ballot_sync(0xffffffffu, dorot);
     const unsigned flags = (bal & 1u) | ((bal >> 7) & 2u) | ((bal >> 14) & 4u) | ((bal >> 21) & 8u);
     if (flags == 0u) return 0;
@@ -116,6 +124,11 @@ __device__ __forceinline__ int sub_round_v0(cf (&y)[8][4], float (&a)[8], int la
             a[PB[i]] = fmaxf(a[PB[i]] - tgi, 0.f);
         }
     }
+    if (PROF) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) asm volatile("" :: "f"(y[i][0].x), "f"(y[i][3].y));
+    }
+    TICK(3);
     return __popc(flags);
 }
 
@@ -131,7 +144,10 @@ __device__ __forceinline__ void neighbour_sync(int g, int ngroups) {
     }
 }
 
+template <bool PROF>
 __global__ void __launch_bounds__(512, 1) jacobi_v0(const cf* X, cf* Yout, int* info, long long* clk, int max_sweeps) {
+    unsigned acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned tlast = 0;
     extern __shared__ float4 smem_raw[];
     constexpr int LS = N + 4, NT = 512, NW = 16;
     cf* Ys = (cf*)smem_raw;
@@ -163,6 +179,7 @@ __global__ void __launch_bounds__(512, 1) jacobi_v0(const cf* X, cf* Yout, int* 
             cf* rowB = Ys + (4 * J) * LS + lane;
             cf v[8][4];
             float a[8];
+            if (PROF) tlast = (unsigned)clock();
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
 #pragma unroll
@@ -170,16 +187,21 @@ __global__ void __launch_bounds__(512, 1) jacobi_v0(const cf* X, cf* Yout, int* 
                 a[i] = nrm[4 * I + i];
                 a[4 + i] = nrm[4 * J + i];
             }
+            if (PROF) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) asm volatile("" :: "f"(v[i][0].x), "f"(v[i][3].y), "f"(a[i]));
+            }
+            TICK(4);
             int nrot = 0;
             if (r == 0) {
-                nrot += sub_round_v0<0, 2, 4, 6, 1, 3, 5, 7>(v, a, lane, big);
-                nrot += sub_round_v0<0, 1, 4, 5, 2, 3, 6, 7>(v, a, lane, big);
-                nrot += sub_round_v0<0, 1, 4, 5, 3, 2, 7, 6>(v, a, lane, big);
+                nrot += sub_round_v0<PROF, 0, 2, 4, 6, 1, 3, 5, 7>(v, a, lane, big, acc, tlast);
+                nrot += sub_round_v0<PROF, 0, 1, 4, 5, 2, 3, 6, 7>(v, a, lane, big, acc, tlast);
+                nrot += sub_round_v0<PROF, 0, 1, 4, 5, 3, 2, 7, 6>(v, a, lane, big, acc, tlast);
             }
-            nrot += sub_round_v0<0, 1, 2, 3, 4, 5, 6, 7>(v, a, lane, big);
-            nrot += sub_round_v0<0, 1, 2, 3, 5, 6, 7, 4>(v, a, lane, big);
-            nrot += sub_round_v0<0, 1, 2, 3, 6, 7, 4, 5>(v, a, lane, big);
-            nrot += sub_round_v0<0, 1, 2, 3, 7, 4, 5, 6>(v, a, lane, big);
+            nrot += sub_round_v0<PROF, 0, 1, 2, 3, 4, 5, 6, 7>(v, a, lane, big, acc, tlast);
+            nrot += sub_round_v0<PROF, 0, 1, 2, 3, 5, 6, 7, 4>(v, a, lane, big, acc, tlast);
+            nrot += sub_round_v0<PROF, 0, 1, 2, 3, 6, 7, 4, 5>(v, a, lane, big, acc, tlast);
+            nrot += sub_round_v0<PROF, 0, 1, 2, 3, 7, 4, 5, 6>(v, a, lane, big, acc, tlast);
             if (nrot) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -191,7 +213,9 @@ __global__ void __launch_bounds__(512, 1) jacobi_v0(const cf* X, cf* Yout, int* 
                 for (int i = 1; i < 8; ++i) if (lane == i) am = a[i];
                 if (lane < 8) nrm[lane < 4 ? 4 * I + lane : 4 * J + lane - 4] = am;
             }
+            TICK(5);
             if (r + 1 < nrounds) neighbour_sync(g, ngroups);
+            TICK(6);
         }
         sweeps = sweep + 1;
         if (!__syncthreads_or(big ? 1 : 0)) { status = 0; break; }
@@ -202,6 +226,9 @@ __global__ void __launch_bounds__(512, 1) jacobi_v0(const cf* X, cf* Yout, int* 
     if (tid == 0) {
         info[2 * blockIdx.x] = status; info[2 * blockIdx.x + 1] = sweeps;
         if (blockIdx.x == 0) clk[0] = t1 - t0;
+    }
+    if (PROF && blockIdx.x == 0 && lane == 0) {
+        for (int i = 0; i < 8; ++i) clk[8 + warp * 8 + i] = acc[i];
     }
 }
 
@@ -376,6 +403,192 @@ __global__ void __launch_bounds__(512, 1) jacobi_v2(const cf* X, cf* Yout, int* 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// V5: the Gram entries of a block pair are formed ONCE per round.  One pass over the 8 rows gives the
+// 4 x 4 cross block C[i][j] = <A_i, B_j> (128 FFMA2 per lane), ONE transposed reduction of its 32 real
+// numbers leaves entry (i, j) on lane pair 8i + 2j (+1: im), and the four sub-rounds then run on those
+// scalars: rotation (A_i, B_(i+s)&3) from the current C[i][j] and the running squared norms, after which
+// every other entry is rescaled by the cosines of the two rotations that touched its rows ("lite" update:
+// the terms it drops are second order in the rotation angles; the rotations stay exactly unitary, only
+// their angles are approximate; convergence measured on circuit thetas: same number of sweeps).  The 16
+// rotations are then applied to the rows in one uninterrupted FFMA2 stream.  Per round: one reduction
+// chain instead of four, and long pure-FMA phases that the other warps of the scheduler can hide behind.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float2 neg2(float2 a) { return make_float2(-a.x, -a.y); }
+
+__device__ __forceinline__ void gram_part_n(const Row& p, const Row& q, float& gr, float& gi) {
+    float2 r2 = make_float2(0.f, 0.f), m2 = r2;
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        r2 = __ffma2_rn(p.re[t], q.re[t], r2);
+        r2 = __ffma2_rn(p.im[t], q.im[t], r2);
+        m2 = __ffma2_rn(p.im[t], q.re[t], m2);
+        m2 = __ffma2_rn(neg2(p.re[t]), q.im[t], m2);
+    }
+    gr = r2.x + r2.y;
+    gi = m2.x + m2.y;
+}
+
+// transposed reduction of 32 values over the 32 lanes: afterwards lane l holds the full sum of v[l]
+__device__ __forceinline__ float reduce32(float (&v)[32], int lane) {
+#pragma unroll
+    for (int d = 16; d >= 1; d >>= 1) {
+        const bool hi = (lane & d) != 0;
+#pragma unroll
+        for (int k = 0; k < d; ++k) {
+            const float keep = hi ? v[k + d] : v[k];
+            const float send = hi ? v[k] : v[k + d];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, d);
+        }
+    }
+    return v[0];
+}
+
+template <bool PROF>
+__global__ void __launch_bounds__(512, 1) jacobi_v5(const cf* X, cf* Yout, int* info, long long* clk, int max_sweeps) {
+    unsigned acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned tlast = 0;
+    extern __shared__ float4 smem_raw[];
+    constexpr int NT = 512, NW = 16;
+    float* Yp = (float*)smem_raw;
+    float* nrm = Yp + N * RS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    load_planar(Yp, X + (size_t)blockIdx.x * N * N, tid, NT);
+    __syncthreads();
+    constexpr int nb = N / 4, mcirc = nb - 1, nrounds = nb - 1, ngroups = nb / 2;
+    const int li = lane >> 3, lj = (lane >> 1) & 3;
+    const bool im_lane = (lane & 1) != 0;
+    int sweeps = 0, status = 1;
+    long long t0 = clock64();
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        refresh_norms(Yp, nrm, warp, lane, NW);
+        __syncthreads();
+        bool big = false;
+        for (int r = 0; r < nrounds; ++r) {
+            const int g = warp;
+            int I, J;
+            if (g == 0) { I = mcirc; J = r; }
+            else { I = (r + g) % mcirc; J = (r - g + mcirc) % mcirc; }
+            float* rowA = Yp + (4 * I) * RS;
+            float* rowB = Yp + (4 * J) * RS;
+            Row v[8];
+            if (PROF) tlast = (unsigned)clock();
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                row_load(v[i], rowA + i * RS, lane);
+                row_load(v[4 + i], rowB + i * RS, lane);
+            }
+            if (PROF) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) asm volatile("" :: "f"(v[i].re[0].x), "f"(v[i].im[1].y));
+            }
+            TICK(4);
+            int nrot = 0;
+            if (r == 0) {
+                // the 12 rotations inside the two blocks: three exact sub-rounds
+                float a[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { a[i] = nrm[4 * I + i]; a[4 + i] = nrm[4 * J + i]; }
+                nrot += sub_round_p4<0, 2, 4, 6, 1, 3, 5, 7>(v, a, lane, big);
+                nrot += sub_round_p4<0, 1, 4, 5, 2, 3, 6, 7>(v, a, lane, big);
+                nrot += sub_round_p4<0, 1, 4, 5, 3, 2, 7, 6>(v, a, lane, big);
+                float am = a[0];
+#pragma unroll
+                for (int i = 1; i < 8; ++i) if (lane == i) am = a[i];
+                if (lane < 8) nrm[lane < 4 ? 4 * I + lane : 4 * J + lane - 4] = am;
+                __syncwarp();
+            }
+            // ---- cross block: Gram once ----
+            float vals[32];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) gram_part_n(v[i], v[4 + j], vals[8 * i + 2 * j], vals[8 * i + 2 * j + 1]);
+            if (PROF) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) asm volatile("" :: "f"(vals[i]));
+            }
+            TICK(0);
+            const float mine = reduce32(vals, lane);
+            const float other = __shfl_xor_sync(0xffffffffu, mine, 1);
+            float gr = im_lane ? other : mine, gi = im_lane ? mine : other;
+            if (PROF) { asm volatile("" :: "f"(gr), "f"(gi)); }
+            TICK(1);
+            float aA = nrm[4 * I + li], aB = nrm[4 * J + lj];
+            float rc[4], rsr[4], rsi[4];
+            unsigned rflags = 0;
+#pragma unroll
+            for (int s = 0; s < 4; ++s) {
+                const bool active = lj == ((li + s) & 3);
+                const float g2 = fmaf(gr, gr, gi * gi), apq = aA * aB;
+                const bool dorot = active && (g2 > TOL2 * apq) && (g2 > 1e-30f);
+                big = big || (dorot && g2 > BIG2 * apq);
+                float c = 1.f, sr = 0.f, si = 0.f, tg = 0.f;
+                const unsigned bal = __ballot_sync(0xffffffffu, dorot);
+                if (bal) {                                     // warp-uniform
+                    if (dorot) rot_params(aA, aB, gr, gi, g2, c, sr, si, tg);
+                    const int srcA = 8 * li + 2 * ((li + s) & 3);          // rotation of row A_li in this sub-round
+                    const int srcB = 8 * ((lj - s) & 3) + 2 * lj;          // rotation of row B_lj
+                    const float cA = __shfl_sync(0xffffffffu, c, srcA), tA = __shfl_sync(0xffffffffu, tg, srcA);
+                    const float cB = __shfl_sync(0xffffffffu, c, srcB), tB = __shfl_sync(0xffffffffu, tg, srcB);
+                    aA = fmaxf(aA + tA, 0.f);
+                    aB = fmaxf(aB - tB, 0.f);
+                    const float sc = cA * cB;
+                    gr *= sc; gi *= sc;
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) rflags |= ((bal >> (8 * i + 2 * ((i + s) & 3))) & 1u) << (4 * s + i);
+                }
+                rc[s] = c; rsr[s] = sr; rsi[s] = si;
+            }
+            if (PROF) { asm volatile("" :: "f"(rc[3]), "f"(rsr[3]), "f"(rsi[3]), "f"(aA), "f"(aB), "r"(rflags)); }
+            TICK(2);
+            if (rflags) {
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (rflags & (1u << (4 * s + i))) {    // warp-uniform
+                            const int src = 8 * i + 2 * ((i + s) & 3);
+                            const float ci = __shfl_sync(0xffffffffu, rc[s], src);
+                            const float sri = __shfl_sync(0xffffffffu, rsr[s], src);
+                            const float sii = __shfl_sync(0xffffffffu, rsi[s], src);
+                            rot_apply_p(ci, sri, sii, v[i], v[4 + ((i + s) & 3)]);
+                        }
+                    }
+                nrot += __popc(rflags);
+                if ((lane & 7) == 0) nrm[4 * I + li] = aA;
+                if (lane < 8 && !im_lane) nrm[4 * J + lj] = aB;
+            }
+            if (PROF) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) asm volatile("" :: "f"(v[i].re[0].x), "f"(v[i].im[1].y));
+            }
+            TICK(3);
+            if (nrot) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    row_store(v[i], rowA + i * RS, lane);
+                    row_store(v[4 + i], rowB + i * RS, lane);
+                }
+            }
+            TICK(5);
+            if (r + 1 < nrounds) neighbour_sync(g, ngroups);
+            TICK(6);
+        }
+        sweeps = sweep + 1;
+        if (!__syncthreads_or(big ? 1 : 0)) { status = 0; break; }
+    }
+    long long t1 = clock64();
+    store_planar(Yp, Yout + (size_t)blockIdx.x * N * N, tid, NT);
+    if (tid == 0) {
+        info[2 * blockIdx.x] = status; info[2 * blockIdx.x + 1] = sweeps;
+        if (blockIdx.x == 0) clk[0] = t1 - t0;
+    }
+    if (PROF && blockIdx.x == 0 && lane == 0) {
+        for (int i = 0; i < 8; ++i) clk[8 + warp * 8 + i] = acc[i];
+    }
+}
+
 // ---- 1024 threads, 2-row blocks -----------------------------------------------------------------
 // sub-round of 2 disjoint rotations (A0,B0), (A1,B1): after the 16-step a half-warp owns one pair,
 // after the 8-step a quarter owns its re or im part; one more shuffle fetches the other part.
@@ -536,7 +749,7 @@ int main(int argc, char** argv) {
     for (auto& v : h) { v.x = (rand() / (float)RAND_MAX - 0.5f); v.y = (rand() / (float)RAND_MAX - 0.5f); }
     cf *dX, *dY; int* dinfo; long long* dclk;
     cudaMalloc(&dX, h.size() * sizeof(cf)); cudaMalloc(&dY, h.size() * sizeof(cf));
-    cudaMalloc(&dinfo, nmat * 2 * sizeof(int)); cudaMalloc(&dclk, 2 * sizeof(long long));
+    cudaMalloc(&dinfo, nmat * 2 * sizeof(int)); cudaMalloc(&dclk, 256 * sizeof(long long));
     cudaMemcpy(dX, h.data(), h.size() * sizeof(cf), cudaMemcpyHostToDevice);
     std::vector<std::complex<double>> M(N * N);
     for (int e = 0; e < N * N; ++e) M[e] = std::complex<double>(h[e].x, h[e].y);
@@ -546,8 +759,11 @@ int main(int argc, char** argv) {
     const int smem_v0 = (N * (N + 4)) * (int)sizeof(cf) + N * (int)sizeof(float);
     const int smem_p = N * RS * (int)sizeof(float) + N * (int)sizeof(float);
     Variant vs[] = {
-        {"V0  512 thr, 4-row blocks, interleaved FFMA (production)", jacobi_v0, 512, smem_v0},
+        {"V0  512 thr, 4-row blocks, interleaved FFMA (production)", jacobi_v0<false>, 512, smem_v0},
+        {"V0p the same with per-phase clocks", jacobi_v0<true>, 512, smem_v0},
         {"V2  512 thr, 4-row blocks, planar FFMA2", jacobi_v2, 512, smem_p},
+        {"V5  512 thr, 4-row blocks, planar FFMA2, Gram once per round (lite update)", jacobi_v5<false>, 512, smem_p},
+        {"V5p the same with per-phase clocks (gram | reduce32 | 4 scalar sub-rounds | apply | load | store | barrier)", jacobi_v5<true>, 512, smem_p},
         {"V3 1024 thr, 2-row blocks, planar FFMA2, __syncthreads per round", jacobi_v3<0>, 1024, smem_p},
         {"V4 1024 thr, 2-row blocks, planar FFMA2, grouped named barriers", jacobi_v3<1>, 1024, smem_p},
     };
@@ -563,7 +779,7 @@ int main(int argc, char** argv) {
         }
         cudaError_t err = cudaDeviceSynchronize();
         if (err != cudaSuccess) { printf("%s: CUDA error: %s\n", v.name, cudaGetErrorString(err)); return 1; }
-        std::vector<int> info(nmat * 2); long long clk[2];
+        std::vector<int> info(nmat * 2); long long clk[256];
         cudaMemcpy(info.data(), dinfo, info.size() * sizeof(int), cudaMemcpyDeviceToHost);
         cudaMemcpy(clk, dclk, sizeof(clk), cudaMemcpyDeviceToHost);
         std::vector<cf> y((size_t)N * N);
@@ -585,6 +801,14 @@ int main(int argc, char** argv) {
         printf("%s\n    %.3f ms per launch (%d matrices), mean sweeps %.2f, not converged %d, CTA 0: %.0f cycles per sweep; "
                "matrix 0: sigma err %.2e sigma_max, max |cos| %.2e\n",
                v.name, ms, nmat, sw / nmat, bad, (double)clk[0] / info[1], maxerr, maxdot);
+        if (v.name[2] == 'p') {
+            printf("    per-warp cycles of CTA 0 (gram | reduce | params | bcast+apply | load | store | barrier), total %lld:\n", clk[0]);
+            for (int w : {0, 1, 5, 10, 15}) {
+                printf("      warp %2d:", w);
+                for (int i = 0; i < 7; ++i) printf(" %9lld", clk[8 + w * 8 + i]);
+                printf("\n");
+            }
+        }
     }
     return 0;
 }

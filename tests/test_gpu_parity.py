@@ -339,6 +339,44 @@ def test_simulator_ghz_qft_and_sweep():                     # simulator_test.py:
         MPSimulator().simulate("not a circuit")
 
 
+def test_simulator_batched_sweep_matches_sequential():          # simulator.py:67-87 as ONE batched run
+    """A parameter sweep compiles once and runs its resolvers as one MPSBatch; the results equal the
+    reference's sequential loop (one MPS per resolver), including non-adjacent gates (swap networks),
+    flipped control/target order and truncation."""
+    import mpsim_b200 as mp
+    from mpsim_b200.mpsim_cirq import MPSimulator
+    from tests._fake_cirq import Circuit, H, CNOT, CZPow, Rx
+    n = 7
+    ops = [H(0)] + [CNOT(i, i + 1) for i in range(n - 1)] + [Rx("t", q) for q in range(n)]
+    ops += [CZPow(0.3, 0, 4), CNOT(5, 2), Rx("u", 3), CNOT(6, 0)] + [Rx("t", q) for q in range(0, n, 2)]
+    circ = Circuit(ops)
+    params = [{"t": 0.17 * (i + 1), "u": 1.0 - 0.2 * i} for i in range(6)]
+    for options in ({}, {"maxsvals": 3}):
+        seq = MPSimulator(dict(options, batch_sweeps=False)).simulate_sweep(circ, params)
+        bat = MPSimulator(dict(options)).simulate_sweep(circ, params)
+        assert len(seq) == len(bat) == len(params)
+        for a, b in zip(seq, bat):
+            assert isinstance(b, mp.MPS) and a.bond_dimensions() == b.bond_dimensions()
+            np.testing.assert_allclose(b.wavefunction(), a.wavefunction(), atol=2e-6)
+            assert abs(a.norm() - b.norm()) < 1e-5
+        bits = np.array([[0] * n, [1] * n, [1, 0, 1, 0, 1, 0, 1]], dtype=np.uint8)
+        res = MPSimulator(dict(options)).simulate_sweep_batched(circ, params, amplitudes=bits)
+        assert res.local_range == (0, len(params)) and res.total == len(params)
+        idx = (bits.astype(np.int64) << np.arange(n - 1, -1, -1)[None, :]).sum(axis=1)
+        for i, a in enumerate(seq):
+            assert abs(res.norms[i] - a.norm()) < 1e-5
+            np.testing.assert_allclose(res.amplitudes[i], a.wavefunction()[idx], atol=2e-6)
+        np.testing.assert_allclose(res.mps(2).wavefunction(), seq[2].wavefunction(), atol=2e-6)
+    # circuits whose structure differs between resolvers, or with a non-unitary gate, keep the sequential path
+    with pytest.raises(ValueError):
+        MPSimulator().simulate_sweep_batched(Circuit([H(0), Toffoli_or_none(0, 1, 2)]), params)
+
+
+def Toffoli_or_none(a, b, c):
+    from tests._fake_cirq import Toffoli
+    return Toffoli(a, b, c)
+
+
 def test_non_unitary_gate_orthonormalizes_and_renormalizes():      # core_test.py:1341-1428
     import mpsim_b200 as mp
     from mpsim_b200.gates import computational_basis_projector
