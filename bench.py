@@ -29,6 +29,10 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+# dram bytes per 128 x 128 job of svd_small_kernel and where that number comes from (ncu --set full capture)
+SVD_SMALL_DRAM_BYTES_PER_JOB = (19.911e6 + 0.046e6) / 148.0
+SVD_SMALL_TRAFFIC_SOURCE = "profiles/r1_svd_small_v5_ncu_full.txt (kernel of commit c774efb; 148 jobs: 19.91 MB read + 0.05 MB written)"
+
 METRIC = "two_qudit_gate_applications_per_sec"
 UNIT = "applications/s"
 
@@ -157,49 +161,65 @@ def _oracle_one_circuit(payload):
     nrm = mps.norm()
     dt = time.perf_counter() - t0
     del ctx
-    return len(ops), dt, nrm
+    smax = np.array([max(float(t["s_kept"].max()) if t["s_kept"].size else 0.0,
+                         float(t["s_trunc"].max()) if t["s_trunc"].size else 0.0) for t in mps.trace])
+    skept_last = np.array([float(t["s_kept"][-1]) if t["s_kept"].size else 0.0 for t in mps.trace])
+    return len(ops), dt, nrm, smax, skept_last
 
 
-def cpu_reference_step(args, ncircuits, nprocs, track_norms, seed0=1000):
-    """ncircuits circuits of the workload through the oracle on nprocs host processes.
+def cpu_reference_step(args, ncircuits, nprocs, track_norms, seed0=1000, pool=None):
+    """ncircuits circuits of the workload through the oracle on nprocs host processes (``pool``: an
+    already running multiprocessing pool -- process start-up stays outside the timed wall).
     Returns (applications, wall seconds)."""
-    import multiprocessing as mp
     payloads = [(args.nqubits, args.depth, args.chi, seed0 + i, track_norms) for i in range(ncircuits)]
     t0 = time.perf_counter()
-    if nprocs <= 1:
+    if pool is None:
         res = [_oracle_one_circuit(p) for p in payloads]
     else:
-        with mp.get_context("fork").Pool(nprocs) as pool:
-            res = pool.map(_oracle_one_circuit, payloads)
+        res = pool.map(_oracle_one_circuit, payloads, chunksize=1)
     wall = time.perf_counter() - t0
+    cpu_reference_step.last = res
     return sum(r[0] for r in res), wall
+
+
+def _pool_ready(_):
+    import numpy  # noqa: F401  (import cost paid before the timed region)
+    from oracle.mps_oracle import OracleMPS  # noqa: F401
+    return os.getpid()
 
 
 def run_reference_arm(args):
     """--impl reference: the reference's CPU implementation of the path (oracle port: the
     reference itself cannot be imported here -- tensornetwork==0.2.1 / cirq absent)
-    on all host cores, one circuit per core per step (1 BLAS thread each)."""
+    on all host cores, one circuit per core per step (1 BLAS thread each).
+    The worker pool is created and warmed before anything is timed; ``--warmup`` untimed steps run
+    first (at least one)."""
+    import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = len(os.sched_getaffinity(0))
     nprocs = max(1, cores)
     ncirc = nprocs
-    for _ in range(args.warmup if args.warmup < 1 else 1):
-        cpu_reference_step(args, ncirc, nprocs, False)
-    apps, wall = 0, 0.0
-    for _ in range(args.steps):
-        a, w = cpu_reference_step(args, ncirc, nprocs, False)
-        apps += a; wall += w
-    value = apps / wall
-    fa, fw = cpu_reference_step(args, ncirc, nprocs, True)
-    sample = (f"{ncirc} circuits per step ({args.nqubits} qubits, depth {args.depth}, chi {args.chi}; "
-              f"{apps // max(args.steps, 1)} applications), complex128 numpy/LAPACK restatement, one process per "
-              f"core with 1 BLAS thread; no per-application norm bookkeeping (conservative: the reference "
-              f"also calls norm() after every application, core.py:1160-1161)")
+    warm = max(1, args.warmup)
+    with mp.get_context("fork").Pool(nprocs) as pool:
+        pool.map(_pool_ready, range(4 * nprocs))
+        for _ in range(warm):
+            cpu_reference_step(args, ncirc, nprocs, False, pool=pool)
+        apps, wall = 0, 0.0
+        for _ in range(args.steps):
+            a, w = cpu_reference_step(args, ncirc, nprocs, False, pool=pool)
+            apps += a; wall += w
+        value = apps / wall
+        fa, fw = cpu_reference_step(args, ncirc, nprocs, True, pool=pool)
+    sample = (f"{ncirc} circuits per step (members 0..{ncirc - 1} of the batched workload: {args.nqubits} qubits, depth "
+              f"{args.depth}, chi {args.chi}; {apps // max(args.steps, 1)} applications), complex128 numpy/LAPACK "
+              f"restatement, one process per core with 1 BLAS thread, pool started before the timed region; no "
+              f"per-application norm bookkeeping (conservative: the reference also calls norm() after every "
+              f"application, core.py:1160-1161)")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
+        "steps": args.steps, "warmup": warm, "ms_per_step": 1e3 * wall / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "complex128",
         "data": "synthetic", "config": workload_config(args, args.gpus),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": nprocs, "kind": "port", "sample": sample,
@@ -221,23 +241,28 @@ def time_dominant_kernel(torch, args, batch, reps=3):
     lib = _lib.load(require_device=True)
     chain = batch._chain
     d, chi, B = 2, args.chi, chain.B
-    site = None
-    for i in range(chain.n - 1):
-        if chain.bonds[i] == chi and chain.bonds[i + 1] == chi and chain.bonds[i + 2] == chi:
-            site = i
-            break
-    if site is None:
+    # disjoint bonds of the full shape (chi, chi, chi) in the middle of the chain
+    sites = [i for i in range(0, chain.n - 1, 2)
+             if chain.bonds[i] == chi and chain.bonds[i + 1] == chi and chain.bonds[i + 2] == chi]
+    if not sites:
         return None
     dev = chain.device
     m = d * chi
+    nsm = torch.cuda.get_device_properties(dev).multi_processor_count
+    # one CTA per matrix and SM: time a whole number of waves, as the launches of the workload are
+    # (a layer of the circuit is ~19 bonds x 512 members = 66 waves; 512 jobs alone would be 3.46)
+    want = 6 * nsm
+    nd = min(len(sites), -(-want // B))
     gates = torch.from_numpy(haar_gates(B, np.random.default_rng(7)).reshape(B, 16)).to(dev)
-    desc = np.zeros(1, dtype=_lib.GATE2_DESC)
-    desc[0] = (chain.site_ptr(site), chain.site_ptr(site + 1), 0, 0, gates.data_ptr(), 0,
-               chain.total, chain.total, 0, 0, 16, 0)
+    desc = np.zeros(nd, dtype=_lib.GATE2_DESC)
+    for t in range(nd):
+        desc[t] = (chain.site_ptr(sites[t]), chain.site_ptr(sites[t] + 1), 0, 0, gates.data_ptr(), 0,
+                   chain.total, chain.total, 0, 0, 16, 0)
     ddesc = _lib.to_device_bytes(desc, dev)
-    nj = min(B, 65535)
-    theta = torch.empty((nj, m, m), dtype=torch.complex64, device=dev)
-    _lib.check(lib.mpsb_theta(ddesc.data_ptr(), 1, nj, d, chi, chi, chi, theta.data_ptr(), None, 0, _lib.stream_ptr()))
+    theta = torch.empty((nd * B, m, m), dtype=torch.complex64, device=dev)
+    _lib.check(lib.mpsb_theta(ddesc.data_ptr(), nd, B, d, chi, chi, chi, theta.data_ptr(), None, 0, _lib.stream_ptr()))
+    nj = min(nd * B, 65535)
+    nj = max(nj // nsm * nsm, min(nj, nsm))
     left = torch.empty((nj, m, chi), dtype=torch.complex64, device=dev)
     right = torch.empty((nj, chi, m), dtype=torch.complex64, device=dev)
     info = torch.zeros((nj, 2), dtype=torch.int32, device=dev)
@@ -257,7 +282,17 @@ def time_dominant_kernel(torch, args, batch, reps=3):
     # mpsb_svd = one strided D2D copy + the SVD kernel; the copy is ~0.1% of the time
     ms = e0.elapsed_time(e1) / reps
     sweeps = float(info[:, 1].float().mean().item())
-    return {"ms_per_launch": ms, "jobs_per_launch": nj, "m": m, "n": m, "mean_sweeps": sweeps}
+    out = {"ms_per_launch": ms, "jobs_per_launch": nj, "m": m, "n": m, "mean_sweeps": sweeps}
+    # profiling build of the library only (MPSB_NVCC_EXTRA=-DMPSB_PROFILE): phase clocks of CTA 0
+    import ctypes
+    if hasattr(lib, "mpsb_debug_phase_clocks"):
+        clk = (ctypes.c_longlong * 32)()
+        if lib.mpsb_debug_phase_clocks(clk) == 0:
+            names = ["load", "qr_R", "jacobi", "sort", "W=XV", "form_Q", "P=QhX", "write"]
+            c = list(clk)
+            out["phase_cycles_cta0"] = {n: c[i + 1] - c[i] for i, n in enumerate(names)}
+            out["sweeps_cta0"] = int(info[0, 1].item())
+    return out
 
 
 def time_secondary(torch, args, batch):
@@ -311,7 +346,47 @@ def time_secondary(torch, args, batch):
     ms = ev(lambda: chain.norms(), reps=3)
     site_bytes = sum(8.0 * chain.site_elems(i) for i in range(chain.n)) * B
     out["norm_chain"] = {"ms": ms, "launches": 2 * chain.n + 2, "gbs_sites_read_once": site_bytes / (ms * 1e-3) / 1e9}
+    # renormalize scale pass (scale_kernel): every site read and written once, 16 d chiL chiR bytes per site
+    ones = torch.ones(B, dtype=torch.float32, device=chain.device)
+    ms = ev(lambda: chain.scale(ones), reps=3)
+    out["scale_kernel"] = {"ms": ms, "gbs": 2.0 * site_bytes / (ms * 1e-3) / 1e9,
+                           "note": "site <- f[b] * site over the whole slab (read + write), HBM bound"}
+    # amplitude_kernel: <bits|psi_b> for 256 bitstrings of every member: one d-slice of every site per amplitude
+    bits = np.random.default_rng(5).integers(0, 2, size=(256, chain.n)).astype(np.uint8)
+    ms = ev(lambda: chain.amplitudes(bits), reps=3)
+    slice_bytes = sum(8.0 * chain.bonds[i] * chain.bonds[i + 1] for i in range(chain.n)) * B * bits.shape[0]
+    out["amplitude_kernel"] = {"ms": ms, "amplitudes": int(B * bits.shape[0]),
+                               "gbs_slices_read": slice_bytes / (ms * 1e-3) / 1e9,
+                               "note": "vector chain per (member, bitstring); the 256 bitstrings of a member re-read its "
+                                       "sites through L2, so this is an L2/latency figure, not HBM"}
     return out
+
+
+def time_wavefunction(torch):
+    """mpsb_wavefunction (chain of cgemm_kernel launches): 8 d^n bytes written, on a
+    24-qubit chi <= 64 state prepared by the library itself."""
+    import mpsim_b200 as mp
+    from mpsim_b200 import circuits
+    n, depth, chi = 24, 12, 64
+    mps = mp.MPS(n)
+    mps._execute([(o.tensor, o.indices, {"maxsvals": chi, "keep_left_canonical": o.keep_left_canonical})
+                  for o in circuits.brickwork(n, depth, seed=9)])
+    mps.wavefunction_device()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 3
+    e0.record()
+    for _ in range(reps):
+        wf = mps.wavefunction_device()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    out_bytes = 8.0 * 2 ** n
+    # the chain materialises every partial product d^i x chi: written and read once each
+    inter = sum(8.0 * 2 ** (i + 1) * mps._chain.bonds[i + 1] for i in range(n)) * 2
+    del wf
+    return {"nqubits": n, "chi": chi, "ms": ms, "gbs_output_written": out_bytes / (ms * 1e-3) / 1e9,
+            "gbs_with_intermediates": (inter) / (ms * 1e-3) / 1e9,
+            "note": "chain of strided complex GEMMs; bytes = 8 d^n written (+ the partial products written and re-read)"}
 
 
 def measure_tf32_peak(torch):
@@ -413,16 +488,21 @@ def time_chi256(torch):
     cp = mps._chain.compile(plan)
     mps._chain.run(cp)
     torch.cuda.synchronize()
-    mps._chain.reset()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    mps._chain.run(cp, upload=False)
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
+    times = []
+    for _ in range(3):
+        mps._chain.reset()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        mps._chain.run(cp, upload=False)
+        e1.record(); torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = float(np.median(times))
     info = cp.info.cpu().numpy()[: len(plan.apps2)]
     fl = sum(flops_svd_lapack(2 * a.chiL, 2 * a.chiR) + flops_theta(2, a.chiL, a.chiM, a.chiR) for a in plan.apps2)
     return {"workload": "100-qubit brickwork depth 20 chi=256 (BASELINE.json configs[2]), one chain",
-            "applications": len(plan.apps2), "ms": ms, "applications_per_sec": len(plan.apps2) / (ms * 1e-3),
+            "applications": len(plan.apps2), "ms": ms, "ms_all_repetitions": times,
+            "applications_per_sec": len(plan.apps2) / (ms * 1e-3),
             "lapack_equivalent_tflops": fl / (ms * 1e-3) / 1e12,
             "svd_not_converged": int((info[:, 0] != 0).sum()), "svd_mean_sweeps": float(info[:, 1].mean())}
 
@@ -445,8 +525,8 @@ def time_chi1024(torch, jobs=4):
     ddesc = _lib.to_device_bytes(desc, "cuda")
     info = torch.zeros((jobs, 2), dtype=torch.int32, device="cuda")
     ws = torch.empty(lib.mpsb_gate2_workspace_bytes(1, jobs, d, chi, chi, chi, chi) + 256, dtype=torch.uint8, device="cuda")
-    ms = None
-    for rep in range(2):
+    times = []
+    for rep in range(4):                                     # first = warm-up
         A.copy_(A0); Bm.copy_(B0)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -454,13 +534,33 @@ def time_chi1024(torch, jobs=4):
         _lib.check(lib.mpsb_apply_gate2(ddesc.data_ptr(), 1, jobs, d, chi, chi, chi, chi, 1, ws.data_ptr(), ws.numel(),
                                         info.data_ptr(), _lib.stream_ptr()), "mpsb_apply_gate2")
         e1.record(); torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1)
+        if rep > 0:
+            times.append(e0.elapsed_time(e1))
+    ms = float(np.median(times))
     inf = info.cpu().numpy()
     fl = (flops_svd_lapack(d * chi, d * chi) + flops_theta(d, chi, chi, chi)) * jobs
     return {"workload": f"{jobs} disjoint bonds at chi=1024 (2048 x 2048 theta, k=1024), random sites",
-            "applications": jobs, "ms": ms, "applications_per_sec": jobs / (ms * 1e-3),
+            "applications": jobs, "ms": ms, "ms_all_repetitions": times, "applications_per_sec": jobs / (ms * 1e-3),
             "lapack_equivalent_tflops": fl / (ms * 1e-3) / 1e12,
             "svd_not_converged": int((inf[:, 0] != 0).sum()), "svd_mean_sweeps": float(inf[:, 1].mean())}
+
+
+def measure_ffma_peak(torch):
+    """FP32 FMA throughput from a register-only microkernel (mpsim_b200/csrc/bench/ffma_peak.cu, built by
+    __graft_entry__.build() into libmpsb_bench.so): (FFMA TFLOP/s, FFMA2 TFLOP/s) or None."""
+    import ctypes
+    path = os.path.join(ROOT, "mpsim_b200", "libmpsb_bench.so")
+    if not os.path.exists(path):
+        return None
+    lib = ctypes.CDLL(path)
+    lib.mpsb_bench_ffma_peak.restype = ctypes.c_int
+    lib.mpsb_bench_ffma_peak.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p]
+    nsm = torch.cuda.get_device_properties(torch.cuda.current_device()).multi_processor_count
+    scratch = torch.empty(2 * nsm * 512, dtype=torch.float32, device="cuda")
+    out = (ctypes.c_double * 2)()
+    rc = lib.mpsb_bench_ffma_peak(out, scratch.data_ptr(), nsm, torch.cuda.current_stream().cuda_stream)
+    torch.cuda.synchronize()
+    return (float(out[0]), float(out[1])) if rc == 0 else None
 
 
 def measure_fp32_peak(torch):
@@ -514,23 +614,35 @@ def run_our_arm(args):
     for b in range(B):
         gates[:, b, :] = circuits.batch_member_gates(nops, lo + b)        # stream seeded 1000 + member
     gates_pinned = torch.from_numpy(gates).pin_memory()
-    norms_host = torch.empty(B, dtype=torch.float32).pin_memory()
+    # results of a step: every circuit's norm and NAMP amplitudes at seeded bitstrings; with N > 1 they are
+    # all-gathered over NCCL INSIDE the timed region (the path's only collective)
+    NAMP = 16
+    amp_bits = np.random.default_rng(77).integers(0, 2, size=(NAMP, n)).astype(np.uint8)
+    norms_host = torch.empty(total, dtype=torch.float32).pin_memory()
+    amps_host = torch.empty((total, NAMP), dtype=torch.complex64).pin_memory()
     h2d = gates_pinned.numel() * 8
-    d2h = B * 4
+    d2h = total * 4 + total * NAMP * 8
+
+    def results():
+        norms = gather_slices(batch.norms_device(), total)
+        amps = gather_slices(batch.amplitudes_device(amp_bits), total)
+        return norms, amps
 
     def step_resident():
         batch.reset()
         batch.run(cp, upload=False)
-        return batch.norms_device()
+        return results()
 
     def step_e2e():
-        # public API with HOST buffers: gates in, norms out
+        # public API with HOST buffers: gates in, norms and amplitudes out
         batch.stage_gates(cp, gates_pinned.numpy())
         batch.reset()
         batch.run(cp, upload=True)
-        norms_host.copy_(batch.norms_device(), non_blocking=True)
+        norms, amps = results()
+        norms_host.copy_(norms, non_blocking=True)
+        amps_host.copy_(amps, non_blocking=True)
         torch.cuda.current_stream().synchronize()
-        return norms_host
+        return norms_host, amps_host
 
     def barrier():
         torch.cuda.synchronize()
@@ -559,7 +671,7 @@ def run_our_arm(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    ms_res, norms = timed(step_resident, args.steps)
+    ms_res, (norms_all, amps_all) = timed(step_resident, args.steps)
     clocks = sampler.stop() if rank == 0 else {}
     status = batch.status(cp)
     not_converged = int((status[..., 0] != 0).sum())
@@ -568,7 +680,6 @@ def run_our_arm(args):
         step_e2e()
     ms_e2e, _ = timed(step_e2e, args.steps)
 
-    norms_all = gather_slices(norms, total)         # the only collective: B x 4 bytes per rank
     apps_per_step_total = napps * total
     value = apps_per_step_total * args.steps / (ms_res * 1e-3)
     e2e_value = apps_per_step_total * args.steps / (ms_e2e * 1e-3)
@@ -584,10 +695,12 @@ def run_our_arm(args):
                 _, _, _, chiL, chiM, chiR, _, _ = L
                 tc = chiL >= 32 and chiR >= 32 and chiM >= 16        # api.cu: theta_uses_tc (d = 2)
                 launches_per_step += (3 if tc else 1) + 1            # theta (split A, split/transpose B, GEMM | FFMA) + SVD
-        launches_per_step += 2 * n + 2                # norm chain: 2 GEMMs per site + init + gather
+        launches_per_step += 2 * n + 2 + 1            # norm chain: 2 GEMMs per site + init + gather; amplitude kernel
         # dominant kernel roofline (measured live, CUDA events on the launching stream)
         dom = time_dominant_kernel(torch, args, batch)
-        fp32_peak = measure_fp32_peak(torch)
+        sgemm_peak = measure_fp32_peak(torch)
+        ffma = measure_ffma_peak(torch)
+        fp32_peak = ffma[0] if ffma else sgemm_peak
         roof = None
         if dom is not None:
             fl = flops_svd_lapack(dom["m"], dom["n"]) * dom["jobs_per_launch"]
@@ -595,20 +708,43 @@ def run_our_arm(args):
             roof = {"kernel": "svd_small_kernel (single-CTA QR + one-sided Jacobi, 128x128 complex64)",
                     "bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                     "frac": achieved / fp32_peak,
-                    # dram__bytes_read.sum + dram__bytes_write.sum of the 148-job capture in
-                    # profiles/r1_svd_small_ncu_full.txt (19.53 MB + 0), scaled to this launch's job count
-                    "traffic": 19.528e6 / 148.0 * dom["jobs_per_launch"],
+                    "peak_source": ("FFMA microkernel (mpsim_b200/csrc/bench/ffma_peak.cu) measured live in this run"
+                                    if ffma else "cuBLAS SGEMM measured live in this run (libmpsb_bench.so missing)"),
+                    "sgemm_tflops_measured_here": sgemm_peak,
+                    "ffma2_tflops_measured_here": ffma[1] if ffma else None,
+                    "frac_of_sgemm": achieved / sgemm_peak,
+                    # dram__bytes_read.sum + dram__bytes_write.sum per job of the 148-job ncu capture named in
+                    # traffic_source, scaled to this launch's job count (not measured by this run)
+                    "traffic": SVD_SMALL_DRAM_BYTES_PER_JOB * dom["jobs_per_launch"],
+                    "traffic_source": SVD_SMALL_TRAFFIC_SOURCE,
                     "note": "achieved = LAPACK-equivalent flops 4(14 mx mn^2 + 8 mn^3) x jobs / CUDA-event launch "
-                            "time; peak = fp32 SGEMM throughput measured live in this run (MEASURED_PEAKS.json "
-                            "records only HBM and bf16); the kernel is FFMA/shuffle bound in shared memory, "
-                            "not HBM bound",
+                            "time over whole waves of thetas taken from the circuits; peak = fp32 FMA throughput "
+                            "of a register-only microkernel measured live (MEASURED_PEAKS.json records only HBM "
+                            "and bf16); the kernel is FMA/latency bound in shared memory, not HBM bound",
                     "ms_per_launch": dom["ms_per_launch"], "jobs_per_launch": dom["jobs_per_launch"],
                     "mean_sweeps": dom["mean_sweeps"]}
+            if "phase_cycles_cta0" in dom:
+                roof["phase_cycles_cta0"] = dom["phase_cycles_cta0"]
+                roof["sweeps_cta0"] = dom["sweeps_cta0"]
         secondary = time_secondary(torch, args, batch)
         roof_theta = None
+        # GPU side of the parity check done in the cpu_baseline leg below: member 0 run alone with its
+        # singular values recorded
+        chk = None
+        if not args.no_cpu_baseline and lo == 0:
+            one = mp.MPSBatch(1, n)
+            cp1 = one.compile(structure, record_svals=True, maxsvals=chi)
+            one.stage_gates(cp1, gates[:, :1])
+            one.run(cp1)
+            sv1 = one.singular_values(cp1)[:, 0]
+            chk = {"norm": float(one.norms()[0]), "smax": sv1.max(axis=1),
+                   "skept_last": np.array([sv1[t, a.k - 1] if a.k > 0 else 0.0 for t, a in enumerate(cp1.plan.apps2)]),
+                   "k": [a.k for a in cp1.plan.apps2], "batch_norm": float(norms_all[0].item())}
+            del one, cp1
         if not args.no_extra:
             del batch
             torch.cuda.empty_cache()
+            secondary["wavefunction"] = time_wavefunction(torch)
             secondary["chi256"] = time_chi256(torch)
             if not args.no_cpu_baseline:
                 secondary["chi256"]["cpu_baseline"] = cpu_dominant_shape(256, 6)
@@ -634,7 +770,22 @@ def run_our_arm(args):
         if not args.no_cpu_baseline:
             a1, w1 = cpu_reference_step(args, args.cpu_baseline_circuits, 1, False)
             a2, w2 = cpu_reference_step(args, args.cpu_baseline_circuits, 1, True)
-            cpu = {"value": a1 / w1, "unit": UNIT, "cores": 1, "kind": "port",
+            # the same oracle run is the checker of member 0 (identical gate arrays): free-running bounds of
+            # tests/test_gpu_baseline.py (a truncated circuit amplifies rounding; per-application parity at
+            # 1e-5 is the teacher-forced test there)
+            parity = None
+            if chk is not None:
+                _, _, o_norm, o_smax, o_last = cpu_reference_step.last[0]
+                e_max = float(np.max(np.abs(chk["smax"] - o_smax) / np.maximum(o_smax, 1e-300)))
+                e_last = float(np.max(np.abs(chk["skept_last"] - o_last) / np.maximum(o_smax, 1e-300)))
+                parity = {"member": 0, "norm_gpu": chk["norm"], "norm_gpu_in_batch": chk["batch_norm"], "norm_oracle": o_norm,
+                          "norm_rel_err": abs(chk["norm"] - o_norm) / o_norm,
+                          "sigma_max_trace_err": e_max, "last_kept_sigma_trace_err": e_last,
+                          "applications": len(chk["k"]), "mode": "free-running, complex64 vs complex128 oracle"}
+                assert abs(chk["norm"] - o_norm) <= 2e-3 * o_norm, parity
+                assert abs(chk["batch_norm"] - chk["norm"]) <= 1e-5 * chk["norm"] + 1e-7, parity
+                assert e_max <= 5e-3 and e_last <= 5e-3, parity
+            cpu = {"value": a1 / w1, "unit": UNIT, "cores": 1, "kind": "port", "parity_check": parity,
                    "sample": f"{args.cpu_baseline_circuits} circuit(s) of the same workload ({a1} applications) "
                              "through the complex128 numpy/LAPACK restatement of mpsim/core.py:950-1161, 1 process, "
                              "1 BLAS thread, without the per-application norm bookkeeping",
@@ -656,8 +807,9 @@ def run_our_arm(args):
             "applications_per_step": apps_per_step_total,
             "svd_not_converged": not_converged, "svd_mean_sweeps": mean_sweeps,
             "norm_mean": float(norms_all.float().mean().item()),
+            "amplitude_abs_mean": float(amps_all.abs().mean().item()),
             "peaks": {"hbm_gbs": peaks.get("hbm_gbs"), "bf16_tflops": peaks.get("bf16_tflops"),
-                      "fp32_tflops_measured_here": fp32_peak},
+                      "fp32_ffma_tflops_measured_here": fp32_peak, "fp32_sgemm_tflops_measured_here": sgemm_peak},
         }
         print(json.dumps(line), flush=True)
     if world > 1:

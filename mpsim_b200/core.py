@@ -283,7 +283,7 @@ class MPS:
             # to reproduce that the plan is cut after each one
             self._execute_tracking(plan, ops)
             return
-        cp = self._chain.compile(plan, record_svals=self._record_svals)
+        cp = self._chain.compile(plan, record_svals=self._record_svals, transient=True)
         self._chain.run(cp)
         self._last = cp
 
@@ -306,7 +306,7 @@ class MPS:
                 a = plan.apps2[idx]
                 kw = {"keep_left_canonical": a.left_canonical, "maxsvals": a.k}
                 sub._add_adjacent(plan.gates[a.gate_index].reshape(d, d, d, d), a.site, kw, a.source_op, a.is_swap)
-            cp = self._chain.compile(sub, record_svals=self._record_svals)
+            cp = self._chain.compile(sub, record_svals=self._record_svals, transient=True)
             self._chain.run(cp)
             self._last = cp
             if kind == 2:

@@ -165,6 +165,19 @@ int mpsb_apply_gate2(const mpsb_gate2_desc* descs_dev, int ndesc, int nbatch,
                      int d, int chiL, int chiM, int chiR, int k, int left_canonical,
                      void* workspace, size_t workspace_bytes, int32_t* info, void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
+    MPSB_ARG(ndesc >= 0 && nbatch >= 0, "apply_gate2: negative counts");
+    if ((long long)ndesc * nbatch > 65535 && nbatch <= 65535) {
+        // the kernels index (descriptor, member) jobs through one 16-bit grid dimension: a longer call
+        // is run as consecutive chunks of descriptors on the same stream and workspace
+        const int per = 65535 / nbatch;
+        for (int off = 0; off < ndesc; off += per) {
+            const int c = ndesc - off < per ? ndesc - off : per;
+            int rc = mpsb_apply_gate2(descs_dev + off, c, nbatch, d, chiL, chiM, chiR, k, left_canonical, workspace,
+                                      workspace_bytes, info ? info + (size_t)off * nbatch * 2 : nullptr, stream);
+            if (rc) return rc;
+        }
+        return 0;
+    }
     int njobs = ndesc * nbatch;
     if (njobs == 0 || chiL == 0 || chiR == 0) return 0;   // empty tensors: nothing to compute
     Gate2Plan p; cf *X, *extra;

@@ -13,6 +13,24 @@ NVCC_FLAGS = [
 ]
 
 
+# measurement aid of bench.py (FFMA peak microkernel): its own small library, never loaded by the package
+BENCH_SOURCES = [os.path.join("bench", "ffma_peak.cu")]
+BENCH_OUT = os.path.join(PKG, "libmpsb_bench.so")
+
+
+def build_bench(force: bool = False) -> str:
+    srcs = [os.path.join(HERE, s) for s in BENCH_SOURCES]
+    if not force and os.path.exists(BENCH_OUT) and all(os.path.getmtime(s) <= os.path.getmtime(BENCH_OUT) for s in srcs):
+        return BENCH_OUT
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    res = subprocess.run([nvcc] + NVCC_FLAGS + srcs + ["-o", BENCH_OUT], stdout=subprocess.PIPE,
+                         stderr=subprocess.STDOUT, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout)
+        raise RuntimeError("nvcc failed building libmpsb_bench.so")
+    return BENCH_OUT
+
+
 def needs_build() -> bool:
     if not os.path.exists(OUT):
         return True
@@ -42,3 +60,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 if __name__ == "__main__":
     print(build(force=True, verbose="-v" in sys.argv))
+    if not os.environ.get("MPSB_LIB_OUT"):
+        print(build_bench(force=True))

@@ -4,8 +4,35 @@
 namespace {
 
 // A'[l][o][r] = sum_p g[o][p] A[l][p][r]     (mpsim/core.py:819-826)
-// One thread per (l, r): reads the d physical components (each a coalesced stream over r),
-// writes d.  Algorithmic traffic: 16*d*chiL*chiR bytes per site.
+// One thread per (l, r) -- or per (l, r, r+1) with 16-byte accesses when chiR is even (VEC = 2; site
+// slots and batch strides are 128-byte aligned): reads the d physical components (each a coalesced
+// stream over r), writes d.  Algorithmic traffic: 16*d*chiL*chiR bytes per site.
+template <int D>
+__device__ __forceinline__ void gate1_vec2(const mpsb_gate1_desc& d, const cf* Ac, cf* Oc, const cf (&g)[D][D]) {
+    const float4* __restrict__ A = reinterpret_cast<const float4*>(Ac);
+    float4* __restrict__ O = reinterpret_cast<float4*>(Oc);
+    const int half = d.chiR >> 1;                              // float4 = two consecutive r
+    const int64_t n = (int64_t)d.chiL * half;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t l = e / half;
+        const int r2 = (int)(e - l * half);
+        const int64_t base = l * D * half + r2;
+        float4 a[D];
+#pragma unroll
+        for (int p = 0; p < D; ++p) a[p] = A[base + (int64_t)p * half];
+#pragma unroll
+        for (int o = 0; o < D; ++o) {
+            cf t0 = cf_make(0.f, 0.f), t1 = cf_make(0.f, 0.f);
+#pragma unroll
+            for (int p = 0; p < D; ++p) {
+                t0 = cf_fma(g[o][p], cf_make(a[p].x, a[p].y), t0);
+                t1 = cf_fma(g[o][p], cf_make(a[p].z, a[p].w), t1);
+            }
+            O[base + (int64_t)o * half] = make_float4(t0.x, t0.y, t1.x, t1.y);
+        }
+    }
+}
+
 template <int D>
 __global__ void __launch_bounds__(256)
 gate1_kernel(const mpsb_gate1_desc* __restrict__ descs, int nbatch) {
@@ -21,6 +48,10 @@ gate1_kernel(const mpsb_gate1_desc* __restrict__ descs, int nbatch) {
 #pragma unroll
         for (int p = 0; p < D; ++p) g[o][p] = G[o * D + p];
     const int chiR = d.chiR;
+    if ((chiR & 1) == 0 && ((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(O)) & 15) == 0) {   // block-uniform
+        gate1_vec2<D>(d, A, O, g);
+        return;
+    }
     const int64_t n = (int64_t)d.chiL * chiR;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         int64_t l = e / chiR;
@@ -48,6 +79,14 @@ scale_kernel(const mpsb_site_ref* __restrict__ sites, int nbatch, int d, const f
     cf* A = (cf*)s.site + (int64_t)bi * s.bs;
     const float f = factors[bi];
     const int64_t n = (int64_t)s.chiL * d * s.chiR;
+    if ((n & 1) == 0 && (reinterpret_cast<uintptr_t>(A) & 15) == 0) {         // 16-byte accesses (block-uniform)
+        float4* A4 = reinterpret_cast<float4*>(A);
+        for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < (n >> 1); e += (int64_t)gridDim.x * blockDim.x) {
+            float4 v = A4[e];
+            A4[e] = make_float4(f * v.x, f * v.y, f * v.z, f * v.w);
+        }
+        return;
+    }
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
         cf v = A[e];
         A[e] = cf_make(f * v.x, f * v.y);

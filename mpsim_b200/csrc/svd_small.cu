@@ -35,7 +35,6 @@ namespace {
 
 constexpr int ST = 512;          // threads per CTA
 constexpr int NW = ST / 32;      // warps: one 8-row group each at nv = 128
-constexpr int EPL = 4;           // elements per lane per row (row length <= 128)
 constexpr int XCH = 32;          // staging chunk of X: columns in step 4, rows in step 5
 constexpr int XS_ELEMS = 128 * (XCH + 1);   // >= XCH * (128 + 4)
 constexpr float BIG2 = 1e-4f * 1e-4f;       // a sweep without a rotation above this is the last
@@ -61,89 +60,144 @@ struct SvdSmallParams {
     int max_sweeps; float tol2; int do_qr; int use_ns;
 };
 
-// (c, s, t|g|) of [[c, s], [-conj(s), c]] diagonalising [[a, g], [conj(g), b]]; s first, then
-// c = sqrt(1 - |s|^2) derived from s (series near 1) so the rotation is unitary to rounding
-// WITHOUT bias -- see tests/_jacobi_model.py:rotation_params.
+// MUFU approximations without the denormal / range wrappers of rsqrtf() and __fdividef(): the
+// arguments below are bounded away from 0 and infinity (the matrix is scaled to max|x| in [1, 2)
+// and a rotation needs |g|^2 > 1e-30)
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// (c, s, t|g|) of [[c, s], [-conj(s), c]] diagonalising [[a, g], [conj(g), b]].
+// With d = a - b, h = sqrt(d^2 + 4|g|^2), w = h + |d|:  |s|^2 = 2|g|^2 / (h w),  c^2 = w / (2h),
+// t|g| = sign(d) 2|g|^2 / w  (the same rotation as t = sign(zeta) / (|zeta| + sqrt(1 + zeta^2)),
+// zeta = d / 2|g|).  s is built from TWO dependent MUFU approximations (rsqrt of h^2, rsqrt of h w;
+// ~2 ulp each) -- this runs on the critical path of every rotation set and the first version's four
+// dependent MUFU + IEEE sqrt cost ~450 cycles per set (scripts/micro/jacobi_variants.cu) -- and
+// c = sqrt(1 - |s|^2) is then DERIVED from the s actually used, so the rotation is unitary to
+// rounding WITHOUT bias whatever the error of the angle (tests/_jacobi_model.py:rotation_params):
+// series near 1, one Newton step on the approximation otherwise (|s|^2 <= 1/2).
 __device__ __forceinline__ void rot_params(float a, float b, float gr, float gi, float g2,
                                            float& c, float& sr, float& si, float& tg) {
-    // The tangent only steers convergence, so it is built from MUFU approximations (rsqrt, rcp:
-    // ~2 ulp) instead of an IEEE division and square root -- every lane runs this code once per
-    // four rotations.  Unitarity does not depend on it: c is derived from the s actually used.
-    float rg = rsqrtf(g2);
-    float zeta = (a - b) * (0.5f * rg);
-    float az = fminf(fabsf(zeta), 1e18f);                    // keeps az^2 finite
-    float z2 = fmaf(az, az, 1.0f);
-    float t = copysignf(__fdividef(1.0f, az + z2 * rsqrtf(z2)), zeta);
-    float ct = (t * rsqrtf(fmaf(t, t, 1.0f))) * rg;
-    sr = ct * gr;
-    si = ct * gi;
-    float h = fmaf(sr, sr, si * si);
-    if (h < 0.0625f) {
-        float poly = fmaf(h, fmaf(h, fmaf(h, fmaf(h, 0.02734375f, 0.0390625f), 0.0625f), 0.125f), 0.5f);
-        c = fmaf(-h, poly, 1.0f);
+    const float d = a - b;
+    const float u = fmaf(d, d, 4.0f * g2);
+    const float h = u * rsqrt_approx(u);
+    const float w = h + fabsf(d);
+    const float k = copysignf(1.41421356f, d) * rsqrt_approx(h * w);
+    sr = gr * k;
+    si = gi * k;
+    tg = copysignf(2.0f * g2 * rcp_approx(w), d);
+    const float hh = fmaf(sr, sr, si * si);
+    if (hh < 0.0625f) {
+        const float poly = fmaf(hh, fmaf(hh, fmaf(hh, fmaf(hh, 0.02734375f, 0.0390625f), 0.0625f), 0.125f), 0.5f);
+        c = fmaf(-hh, poly, 1.0f);
     } else {
-        c = sqrtf(fmaf(-sr, sr, fmaf(-si, si, 1.0f)));       // large rotations (first sweeps only)
+        const float y = fmaf(-sr, sr, fmaf(-si, si, 1.0f));     // in [~1/2, 15/16]
+        const float r0 = rsqrt_approx(y);
+        const float c0 = y * r0;
+        c = fmaf(0.5f * r0, fmaf(-c0, c0, y), c0);               // Newton: c0 + (y - c0^2) / (2 c0)
     }
-    tg = t * (g2 * rg);
 }
 
-__device__ __forceinline__ void rot_apply(float c, float sr, float si, cf& p, cf& q) {
-    cf np_, nq_;
-    np_.x = fmaf(c, p.x, fmaf(sr, q.x, -(si * q.y)));
-    np_.y = fmaf(c, p.y, fmaf(sr, q.y, si * q.x));
-    nq_.x = fmaf(c, q.x, -fmaf(sr, p.x, si * p.y));
-    nq_.y = fmaf(c, q.y, fmaf(si, p.x, -(sr * p.y)));
-    p = np_;
-    q = nq_;
+// ---- sweep engine: rows in PLANAR layout, packed fma.rn.f32x2 ------------------------------------
+// Row i of Y lives at (float*)(Ys + i * LS): W real parts, then W imaginary parts (W = LC = 64 or
+// 128).  Lane l holds elements 2 NP l .. 2 NP l + 2 NP - 1 of a row (NP = W / 64 float2 pairs of
+// real and of imaginary parts): one LDS.128 (NP = 2) or LDS.64 per plane, and every FFMA2 works on
+// two elements (half the issue slots of the scalar FFMA version for the same FMA-pipe time).
+template <int NP> struct PRow { float2 re[NP], im[NP]; };
+
+template <int NP>
+__device__ __forceinline__ void prow_load(PRow<NP>& r, const float* p, int lane) {
+    if (NP == 2) {
+        const float4 x = *reinterpret_cast<const float4*>(p + 4 * lane);
+        const float4 y = *reinterpret_cast<const float4*>(p + 128 + 4 * lane);
+        r.re[0] = make_float2(x.x, x.y); r.re[NP - 1] = make_float2(x.z, x.w);
+        r.im[0] = make_float2(y.x, y.y); r.im[NP - 1] = make_float2(y.z, y.w);
+    } else {
+        r.re[0] = *reinterpret_cast<const float2*>(p + 2 * lane);
+        r.im[0] = *reinterpret_cast<const float2*>(p + 64 + 2 * lane);
+    }
+}
+template <int NP>
+__device__ __forceinline__ void prow_store(const PRow<NP>& r, float* p, int lane) {
+    if (NP == 2) {
+        *reinterpret_cast<float4*>(p + 4 * lane) = make_float4(r.re[0].x, r.re[0].y, r.re[NP - 1].x, r.re[NP - 1].y);
+        *reinterpret_cast<float4*>(p + 128 + 4 * lane) = make_float4(r.im[0].x, r.im[0].y, r.im[NP - 1].x, r.im[NP - 1].y);
+    } else {
+        *reinterpret_cast<float2*>(p + 2 * lane) = r.re[0];
+        *reinterpret_cast<float2*>(p + 64 + 2 * lane) = r.im[0];
+    }
 }
 
-// One sub-round on the rows of a group: 4 disjoint pairs (A_i, B_i).  The four Gram entries are
-// reduced together; lane l then computes the rotation of pair (l >> 3) only and the parameters
-// are exchanged by shuffles (4x fewer scalar instructions than every lane doing all four).
-template <int A0, int A1, int A2, int A3, int B0, int B1, int B2, int B3>
-__device__ __forceinline__ int sub_round_y(cf (&y)[8][EPL], float (&a)[8], float tol2, int lane, bool& big) {
+__device__ __forceinline__ float2 neg2(float2 v) { return make_float2(-v.x, -v.y); }
+
+// this lane's part of <p, q> = sum p conj(q)
+template <int NP>
+__device__ __forceinline__ void gram_part(const PRow<NP>& p, const PRow<NP>& q, float& gr, float& gi) {
+    float2 r2 = make_float2(0.f, 0.f), m2 = r2;
+#pragma unroll
+    for (int t = 0; t < NP; ++t) {
+        r2 = __ffma2_rn(p.re[t], q.re[t], r2);
+        r2 = __ffma2_rn(p.im[t], q.im[t], r2);
+        m2 = __ffma2_rn(p.im[t], q.re[t], m2);
+        m2 = __ffma2_rn(neg2(p.re[t]), q.im[t], m2);       // the negation folds into the FFMA2 operand
+    }
+    gr = r2.x + r2.y;
+    gi = m2.x + m2.y;
+}
+
+// [p; q] <- [[c, s], [-conj(s), c]] [p; q]; the same nesting of roundings as the scalar form
+//   re p' = fma(c, p.re, fma(s.re, q.re, -(s.im q.im)))   etc.
+template <int NP>
+__device__ __forceinline__ void rot_apply(float c, float sr, float si, PRow<NP>& p, PRow<NP>& q) {
+    const float2 C2 = make_float2(c, c), S2 = make_float2(sr, sr), I2 = make_float2(si, si);
+    const float2 NS2 = make_float2(-sr, -sr), NI2 = make_float2(-si, -si);
+#pragma unroll
+    for (int t = 0; t < NP; ++t) {
+        const float2 pre = p.re[t], pim = p.im[t], qre = q.re[t], qim = q.im[t];
+        p.re[t] = __ffma2_rn(C2, pre, __ffma2_rn(S2, qre, __fmul2_rn(NI2, qim)));
+        p.im[t] = __ffma2_rn(C2, pim, __ffma2_rn(S2, qim, __fmul2_rn(I2, qre)));
+        q.re[t] = __ffma2_rn(C2, qre, __ffma2_rn(NS2, pre, __fmul2_rn(NI2, pim)));
+        q.im[t] = __ffma2_rn(C2, qim, __ffma2_rn(I2, pre, __fmul2_rn(NS2, pim)));
+    }
+}
+
+// transposed reduction of 4 values: afterwards every lane of octet i holds the full sum of g[i]
+__device__ __forceinline__ float reduce4(const float (&g)[4], int lane) {
+    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0;
+    float k0 = h16 ? g[2] : g[0], k1 = h16 ? g[3] : g[1];
+    const float s0 = h16 ? g[0] : g[2], s1 = h16 ? g[1] : g[3];
+    k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+    k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+    float k = h8 ? k1 : k0;
+    const float sd = h8 ? k0 : k1;
+    k += __shfl_xor_sync(0xffffffffu, sd, 8);
+    k += __shfl_xor_sync(0xffffffffu, k, 4);
+    k += __shfl_xor_sync(0xffffffffu, k, 2);
+    k += __shfl_xor_sync(0xffffffffu, k, 1);
+    return k;
+}
+
+// One sub-round on the 8 rows of a group: 4 disjoint pairs (A_i, B_i).  The four Gram entries are
+// reduced together (transposed: 12 shuffles instead of 40); the lanes of octet i compute the rotation
+// of pair i and the parameters are exchanged by shuffles.
+// Measured and NOT adopted (scripts/micro/jacobi_variants.cu V5; production A/B in DESIGN.md 4.1): forming
+// the 16 cross Gram entries of a block pair once per round and updating them by the cosines of the
+// rotations ("lite" update) -- one reduction chain per round instead of four, 30 % fewer instructions,
+// 4 % faster per sweep, but two more sweeps on graded spectra.
+template <int NP, int A0, int A1, int A2, int A3, int B0, int B1, int B2, int B3>
+__device__ __forceinline__ int sub_round(PRow<NP> (&y)[8], float (&a)[8], float tol2, int lane, bool& big) {
     constexpr int PA[4] = {A0, A1, A2, A3}, PB[4] = {B0, B1, B2, B3};
     float gr[4], gi[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        float r = 0.f, m = 0.f;
-#pragma unroll
-        for (int t = 0; t < EPL; ++t) {
-            cf p = y[PA[i]][t], q = y[PB[i]][t];
-            r = fmaf(p.x, q.x, r); r = fmaf(p.y, q.y, r);
-            m = fmaf(p.y, q.x, m); m = fmaf(-p.x, q.y, m);
-        }
-        gr[i] = r; gi[i] = m;
-    }
-    // Transposed reduction: 12 shuffles instead of 40.  After the 16- and 8-steps every lane
-    // owns ONE of the four pairs (pair index = lane >> 3), the 4/2/1 butterfly finishes it.
-    const bool h16 = (lane & 16) != 0, h8 = (lane & 8) != 0;
-    float mgr, mgi;
-    {
-        float k0 = h16 ? gr[2] : gr[0], k1 = h16 ? gr[3] : gr[1];
-        float s0 = h16 ? gr[0] : gr[2], s1 = h16 ? gr[1] : gr[3];
-        k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-        k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-        float k = h8 ? k1 : k0, sd = h8 ? k0 : k1;
-        k += __shfl_xor_sync(0xffffffffu, sd, 8);
-        k += __shfl_xor_sync(0xffffffffu, k, 4);
-        k += __shfl_xor_sync(0xffffffffu, k, 2);
-        k += __shfl_xor_sync(0xffffffffu, k, 1);
-        mgr = k;
-    }
-    {
-        float k0 = h16 ? gi[2] : gi[0], k1 = h16 ? gi[3] : gi[1];
-        float s0 = h16 ? gi[0] : gi[2], s1 = h16 ? gi[1] : gi[3];
-        k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
-        k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
-        float k = h8 ? k1 : k0, sd = h8 ? k0 : k1;
-        k += __shfl_xor_sync(0xffffffffu, sd, 8);
-        k += __shfl_xor_sync(0xffffffffu, k, 4);
-        k += __shfl_xor_sync(0xffffffffu, k, 2);
-        k += __shfl_xor_sync(0xffffffffu, k, 1);
-        mgi = k;
-    }
-    // this lane's pair: index lane >> 3 (all 8 lanes of an octet hold bitwise identical sums)
+    for (int i = 0; i < 4; ++i) gram_part<NP>(y[PA[i]], y[PB[i]], gr[i], gi[i]);
+    const float mgr = reduce4(gr, lane), mgi = reduce4(gi, lane);
     const int sel = lane >> 3;
     float ap = a[PA[0]], aq = a[PB[0]];
 #pragma unroll
@@ -166,8 +220,7 @@ __device__ __forceinline__ int sub_round_y(cf (&y)[8][EPL], float (&a)[8], float
             const float sri = __shfl_sync(0xffffffffu, sr, 8 * i);
             const float sii = __shfl_sync(0xffffffffu, si, 8 * i);
             const float tgi = __shfl_sync(0xffffffffu, tg, 8 * i);
-#pragma unroll
-            for (int t = 0; t < EPL; ++t) rot_apply(ci, sri, sii, y[PA[i]][t], y[PB[i]][t]);
+            rot_apply<NP>(ci, sri, sii, y[PA[i]], y[PB[i]]);
             a[PA[i]] = fmaxf(a[PA[i]] + tgi, 0.f);
             a[PB[i]] = fmaxf(a[PB[i]] - tgi, 0.f);
         }
@@ -379,77 +432,191 @@ __device__ __noinline__ void householder(cf* A, int LS, int nrows, int ncols, in
     __syncthreads();
 }
 
-// Orthonormalisation of W [nv][k] (k <= 64) by one Newton-Schulz step, Q = W (3/2 I - 1/2 W^H W):
-// two small GEMMs instead of the 2k barrier-separated Householder steps.  W = X V_k S^-1 is
-// orthonormal up to E = W^H W - I with |E_ij| ~ 3e-6 sigma_i/sigma_j; the step squares that
-// (||Q^H Q - I|| <= 3/4 ||E||^2) and keeps span(Q) = span(W).  Only taken when ||E||_F < 2e-3
-// (measured on the data, block-uniform); otherwise W is left untouched and the caller runs the
-// Householder path, which also handles zero / noise columns.  M: scratch of 64 x 64.
+// Step 2 of the kernel: one-sided Jacobi sweeps on the first 4 nb rows of Y (nb even), which are
+// converted IN PLACE from interleaved complex to the planar layout of the sweep engine (a row keeps
+// its slot of LS complex numbers: W = LC reals, then W imaginaries) and stay planar afterwards.
+// 4-row blocks are paired by the circle method; a warp owns a pair of blocks per round, keeps its 8
+// rows in registers and does the 16 cross rotations of the pair (plus the 12 inside the two blocks in
+// the first round of a sweep) in sub-rounds of 4 disjoint rotations.  Squared row norms are cached in
+// shared memory, refreshed once per sweep and updated by +-t|g| in between.
+// Rounds are separated by PAIRWISE named barriers, not by a block-wide one: in the circle method
+// group g takes its two blocks of the next round from groups g-1 and g+1 only, so a warp syncs with
+// its two neighbours (edge (g, g+1) = barrier 1 + g, even warps right edge first, odd warps left edge
+// first).  (Polling per-block round counters in shared memory was tried and was 3x slower.)
+// A sweep in which no rotation exceeded cos 1e-4 is the last one.
+template <int NP>
+__device__ __noinline__ void jacobi_sweeps(cf* Ys, int LS, float* nrm, int nb, int max_sweeps, float tol2,
+                                           int& sweeps_out, int& status_out) {
+    constexpr int W = 64 * NP;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int mcirc = nb - 1, ngroups = nb / 2, nrounds = nb > 2 ? nb - 1 : 1;
+    // interleaved -> planar, a row at a time (all of a row is in registers before any of it is written)
+    for (int i = warp; i < 4 * nb; i += NW) {
+        float* row = reinterpret_cast<float*>(Ys + (size_t)i * LS);
+        if (NP == 2) {
+            const float4 x0 = reinterpret_cast<const float4*>(row)[2 * lane];
+            const float4 x1 = reinterpret_cast<const float4*>(row)[2 * lane + 1];
+            __syncwarp();
+            *reinterpret_cast<float4*>(row + 4 * lane) = make_float4(x0.x, x0.z, x1.x, x1.z);
+            *reinterpret_cast<float4*>(row + W + 4 * lane) = make_float4(x0.y, x0.w, x1.y, x1.w);
+        } else {
+            const float4 x0 = reinterpret_cast<const float4*>(row)[lane];
+            __syncwarp();
+            *reinterpret_cast<float2*>(row + 2 * lane) = make_float2(x0.x, x0.z);
+            *reinterpret_cast<float2*>(row + W + 2 * lane) = make_float2(x0.y, x0.w);
+        }
+    }
+    __syncthreads();
+    int sweeps = 0, status = 1;
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        // refresh the cached squared norms
+        for (int i = warp; i < 4 * nb; i += NW) {
+            PRow<NP> r;
+            prow_load<NP>(r, reinterpret_cast<const float*>(Ys + (size_t)i * LS), lane);
+            float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < NP; ++t) { s2 = __ffma2_rn(r.re[t], r.re[t], s2); s2 = __ffma2_rn(r.im[t], r.im[t], s2); }
+            const float sum = warp_sum(s2.x + s2.y);
+            if (lane == 0) nrm[i] = sum;
+        }
+        __syncthreads();
+        bool big = false;
+        for (int r = 0; r < nrounds; ++r) {
+            const int g = warp;
+            if (g < ngroups) {
+                int I, Jb;
+                if (nb == 2) { I = 0; Jb = 1; }
+                else if (g == 0) { I = mcirc; Jb = r; }
+                else { I = (r + g) % mcirc; Jb = (r - g + mcirc) % mcirc; }
+                float* rowA = reinterpret_cast<float*>(Ys + (size_t)(4 * I) * LS);
+                float* rowB = reinterpret_cast<float*>(Ys + (size_t)(4 * Jb) * LS);
+                const int rs = 2 * LS;                           // row stride in floats
+                PRow<NP> v[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    prow_load<NP>(v[i], rowA + i * rs, lane);
+                    prow_load<NP>(v[4 + i], rowB + i * rs, lane);
+                }
+                float a[8];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { a[i] = nrm[4 * I + i]; a[4 + i] = nrm[4 * Jb + i]; }
+                int nrot = 0;
+                if (r == 0) {                                    // inside the two blocks
+                    nrot += sub_round<NP, 0, 2, 4, 6, 1, 3, 5, 7>(v, a, tol2, lane, big);
+                    nrot += sub_round<NP, 0, 1, 4, 5, 2, 3, 6, 7>(v, a, tol2, lane, big);
+                    nrot += sub_round<NP, 0, 1, 4, 5, 3, 2, 7, 6>(v, a, tol2, lane, big);
+                }
+                nrot += sub_round<NP, 0, 1, 2, 3, 4, 5, 6, 7>(v, a, tol2, lane, big);
+                nrot += sub_round<NP, 0, 1, 2, 3, 5, 6, 7, 4>(v, a, tol2, lane, big);
+                nrot += sub_round<NP, 0, 1, 2, 3, 6, 7, 4, 5>(v, a, tol2, lane, big);
+                nrot += sub_round<NP, 0, 1, 2, 3, 7, 4, 5, 6>(v, a, tol2, lane, big);
+                if (nrot) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        prow_store<NP>(v[i], rowA + i * rs, lane);
+                        prow_store<NP>(v[4 + i], rowB + i * rs, lane);
+                    }
+                    float am = a[0];
+#pragma unroll
+                    for (int i = 1; i < 8; ++i) if (lane == i) am = a[i];
+                    if (lane < 8) nrm[lane < 4 ? 4 * I + lane : 4 * Jb + lane - 4] = am;
+                }
+                if (r + 1 < nrounds) {
+                    const bool has_r = g + 1 < ngroups, has_l = g > 0;
+                    if (g & 1) {
+                        if (has_l) named_barrier_sync(g, 64);
+                        if (has_r) named_barrier_sync(g + 1, 64);
+                    } else {
+                        if (has_r) named_barrier_sync(g + 1, 64);
+                        if (has_l) named_barrier_sync(g, 64);
+                    }
+                }
+            }
+        }
+        sweeps = sweep + 1;
+        if (!__syncthreads_or(big ? 1 : 0)) { status = 0; break; }
+    }
+    sweeps_out = sweeps;
+    status_out = status;
+}
+
+// Orthonormalisation of W [nv][k] (k <= 64) by Newton-Schulz steps, W <- W (3/2 I - 1/2 W^H W): two
+// small GEMMs per step instead of the 2k barrier-separated Householder steps.  W = X V_k S^-1 is
+// orthonormal up to E = W^H W - I with |E_ij| ~ 3e-6 sigma_i / sigma_j (a few 1e-3 in Frobenius norm
+// on the thetas of a chi = 64 circuit); a step squares that (||E'|| <= 3/4 ||E||^2) and keeps
+// span(W), and the split only depends on span(Q) (Q Q^H X is the projection either way; the basis
+// inside the span is a gauge choice).  Steps are taken while ||E||_F < 0.05 (measured on the data,
+// block-uniform), the last one from ||E||_F < 1e-3 (-> below 1e-6), at most three; a W further from
+// orthonormal (zero / noise columns, sigma_k ~ 1e-6 sigma_1) is left to the Householder path, which
+// completes the basis as LAPACK does.  Returns true when W is orthonormal.  M: scratch of 64 x 64.
 __device__ bool newton_schulz_q(cf* W, int LS, int nv, int k, cf* M, float* red) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    {
-        const int j = tid >> 3, jb = (tid & 7) * 8;            // G[j][jb .. jb+7]
-        cf acc[8];
+    for (int step = 0; step < 3; ++step) {
+        {
+            const int j = tid >> 3, jb = (tid & 7) * 8;            // G[j][jb .. jb+7]
+            cf acc[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) acc[u] = cf_make(0.f, 0.f);
-        if (j < k && jb < k) {
-            for (int a = 0; a < nv; ++a) {
-                const cf* wr = W + (size_t)a * LS;
-                const cf wj = wr[j];
-                const float4* w4 = reinterpret_cast<const float4*>(wr + jb);      // rows are 16-byte aligned (LS even)
+            for (int u = 0; u < 8; ++u) acc[u] = cf_make(0.f, 0.f);
+            if (j < k && jb < k) {
+                for (int a = 0; a < nv; ++a) {
+                    const cf* wr = W + (size_t)a * LS;
+                    const cf wj = wr[j];
+                    const float4* w4 = reinterpret_cast<const float4*>(wr + jb);      // rows are 16-byte aligned (LS even)
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const float4 v = w4[u];
-                    acc[2 * u] = cf_fma_conja(wj, cf_make(v.x, v.y), acc[2 * u]);
-                    acc[2 * u + 1] = cf_fma_conja(wj, cf_make(v.z, v.w), acc[2 * u + 1]);
+                    for (int u = 0; u < 4; ++u) {
+                        const float4 v = w4[u];
+                        acc[2 * u] = cf_fma_conja(wj, cf_make(v.x, v.y), acc[2 * u]);
+                        acc[2 * u + 1] = cf_fma_conja(wj, cf_make(v.z, v.w), acc[2 * u + 1]);
+                    }
                 }
             }
+            float e2 = 0.f;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool ok = j < k && jb + u < k;
+                cf e = acc[u];
+                if (j == jb + u) e.x -= 1.0f;
+                if (ok) e2 += cf_abs2(e);
+                // M = 3/2 I - 1/2 G  (zero outside the k x k block)
+                M[j * 64 + jb + u] = ok ? cf_make((j == jb + u ? 1.5f : 0.f) - 0.5f * acc[u].x, -0.5f * acc[u].y) : cf_make(0.f, 0.f);
+            }
+            e2 = warp_sum(e2);
+            if (lane == 0) red[warp] = e2;
         }
+        __syncthreads();
         float e2 = 0.f;
 #pragma unroll
-        for (int u = 0; u < 8; ++u) {
-            const bool ok = j < k && jb + u < k;
-            cf e = acc[u];
-            if (j == jb + u) e.x -= 1.0f;
-            if (ok) e2 += cf_abs2(e);
-            // M = 3/2 I - 1/2 G  (zero outside the k x k block)
-            M[j * 64 + jb + u] = ok ? cf_make((j == jb + u ? 1.5f : 0.f) - 0.5f * acc[u].x, -0.5f * acc[u].y) : cf_make(0.f, 0.f);
-        }
-        e2 = warp_sum(e2);
-        if (lane == 0) red[warp] = e2;
-    }
-    __syncthreads();
-    float e2 = 0.f;
+        for (int w = 0; w < NW; ++w) e2 += red[w];
+        if (!(e2 < 0.05f * 0.05f)) { __syncthreads(); return false; }       // also catches NaN
+        {
+            const int a = tid >> 2, jq = (tid & 3) * 16;           // Q[a][jq .. jq+15]
+            cf acc[16];
 #pragma unroll
-    for (int w = 0; w < NW; ++w) e2 += red[w];
-    if (!(e2 < 2e-3f * 2e-3f)) { __syncthreads(); return false; }       // also catches NaN
-    {
-        const int a = tid >> 2, jq = (tid & 3) * 16;           // Q[a][jq .. jq+15]
-        cf acc[16];
+            for (int u = 0; u < 16; ++u) acc[u] = cf_make(0.f, 0.f);
+            if (a < nv && jq < k) {
+                const cf* wr = W + (size_t)a * LS;
+                for (int jp = 0; jp < k; ++jp) {
+                    const cf w = wr[jp];
+                    const float4* m4 = reinterpret_cast<const float4*>(M + jp * 64 + jq);
 #pragma unroll
-        for (int u = 0; u < 16; ++u) acc[u] = cf_make(0.f, 0.f);
-        if (a < nv && jq < k) {
-            const cf* wr = W + (size_t)a * LS;
-            for (int jp = 0; jp < k; ++jp) {
-                const cf w = wr[jp];
-                const float4* m4 = reinterpret_cast<const float4*>(M + jp * 64 + jq);
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    const float4 v = m4[u];
-                    acc[2 * u] = cf_fma(w, cf_make(v.x, v.y), acc[2 * u]);
-                    acc[2 * u + 1] = cf_fma(w, cf_make(v.z, v.w), acc[2 * u + 1]);
+                    for (int u = 0; u < 8; ++u) {
+                        const float4 v = m4[u];
+                        acc[2 * u] = cf_fma(w, cf_make(v.x, v.y), acc[2 * u]);
+                        acc[2 * u + 1] = cf_fma(w, cf_make(v.z, v.w), acc[2 * u + 1]);
+                    }
                 }
             }
-        }
-        __syncthreads();                                       // every read of W is done
-        if (a < nv) {
+            __syncthreads();                                       // every read of W (and of red) is done
+            if (a < nv) {
 #pragma unroll
-            for (int u = 0; u < 16; ++u)
-                if (jq + u < k) W[(size_t)a * LS + jq + u] = acc[u];
+                for (int u = 0; u < 16; ++u)
+                    if (jq + u < k) W[(size_t)a * LS + jq + u] = acc[u];
+            }
         }
+        __syncthreads();
+        if (e2 < 1e-3f * 1e-3f) return true;                       // this step brought ||E||_F below 1e-6
     }
-    __syncthreads();
-    return true;
+    return true;                                                   // 0.05 -> 1.9e-3 -> 2.7e-6 -> 5e-12
 }
 
 __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
@@ -497,107 +664,40 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
 
     PHASE_MARK(1);
     // ---- step 1: Householder QR, R only ------------------------------------------------------
-    if (P.do_qr) householder<0>(Ys, LS, nv, L, min(nv - 1, L), vbuf, scal, nullptr, nullptr);
+    // In panels of 32 steps on the shrinking trailing matrix: a thread owns a fixed column slice for a
+    // whole call, so in one call over all 127 steps the owners of finished columns idle (half of the
+    // threads on average); every new call spreads the remaining columns over all 512 threads again
+    // (threads per column 4 -> 4 -> 8 -> 16).
+    if (P.do_qr) {
+        const int nsteps = min(nv - 1, L);
+        for (int j0 = 0; j0 < nsteps;) {
+            const int chunk = nsteps - j0 > 48 ? 32 : nsteps - j0;
+            householder<0>(Ys + (size_t)j0 * LS + j0, LS, nv - j0, L - j0, chunk, vbuf, scal, nullptr, nullptr);
+            j0 += chunk;
+        }
+    }
 
     PHASE_MARK(2);
     // ---- step 2: one-sided Jacobi on the rows of Y -------------------------------------------
     const int nact = P.do_qr ? min(nv, L) : nv;    // rows >= L of R are exactly zero
     const int nb = 2 * ((nact + 7) / 8);           // 4-row blocks (even count)
-    const int mcirc = nb - 1;
-    const int ngroups = nb / 2;
-    const int nrounds = nb > 2 ? nb - 1 : 1;
-    const int ylanes = P.LC / 32;
     int sweeps = 0, status = 0;
     if (nact >= 2) {
-        status = 1;
-        for (int sweep = 0; sweep < P.max_sweeps; ++sweep) {
-            // refresh the cached squared norms (they are updated by +-t|g| within the sweep)
-            for (int i = warp; i < 4 * nb; i += NW) {
-                const cf* yr = Ys + (size_t)i * LS;
-                float s2 = 0.f;
-#pragma unroll
-                for (int t = 0; t < EPL; ++t)
-                    if (t < ylanes) s2 += cf_abs2(yr[lane + 32 * t]);
-                s2 = warp_sum(s2);
-                if (lane == 0) nrm[i] = s2;
-            }
-            __syncthreads();
-            bool big = false;
-            // Rounds are separated by PAIRWISE named barriers, not by a block-wide one: in the circle
-            // method group g takes its two blocks of the next round from groups g-1 and g+1 only, so
-            // a warp syncs with its two neighbours (edge (g, g+1) = barrier 1 + g, even warps right
-            // edge first, odd warps left edge first) and the warps drift apart by whole rounds; their
-            // shuffle / MUFU latencies then overlap instead of all of them stalling in the same phase.
-            // (Polling per-block round counters in shared memory was tried and was 3x slower.)
-            for (int r = 0; r < nrounds; ++r) {
-                for (int g = warp; g < ngroups; g += NW) {
-                    int I, Jb;
-                    if (nb == 2) { I = 0; Jb = 1; }
-                    else if (g == 0) { I = mcirc; Jb = r; }
-                    else { I = (r + g) % mcirc; Jb = (r - g + mcirc) % mcirc; }
-                    cf* rowA = Ys + (size_t)(4 * I) * LS + lane;
-                    cf* rowB = Ys + (size_t)(4 * Jb) * LS + lane;
-                    cf v[8][EPL];
-                    float a[8];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                        for (int t = 0; t < EPL; ++t) {
-                            v[i][t] = (t < ylanes) ? rowA[(size_t)i * LS + 32 * t] : cf_make(0.f, 0.f);
-                            v[4 + i][t] = (t < ylanes) ? rowB[(size_t)i * LS + 32 * t] : cf_make(0.f, 0.f);
-                        }
-                        a[i] = nrm[4 * I + i];
-                        a[4 + i] = nrm[4 * Jb + i];
-                    }
-                    int nrot = 0;
-                    if (r == 0) {
-                        nrot += sub_round_y<0, 2, 4, 6, 1, 3, 5, 7>(v, a, P.tol2, lane, big);
-                        nrot += sub_round_y<0, 1, 4, 5, 2, 3, 6, 7>(v, a, P.tol2, lane, big);
-                        nrot += sub_round_y<0, 1, 4, 5, 3, 2, 7, 6>(v, a, P.tol2, lane, big);
-                    }
-                    nrot += sub_round_y<0, 1, 2, 3, 4, 5, 6, 7>(v, a, P.tol2, lane, big);
-                    nrot += sub_round_y<0, 1, 2, 3, 5, 6, 7, 4>(v, a, P.tol2, lane, big);
-                    nrot += sub_round_y<0, 1, 2, 3, 6, 7, 4, 5>(v, a, P.tol2, lane, big);
-                    nrot += sub_round_y<0, 1, 2, 3, 7, 4, 5, 6>(v, a, P.tol2, lane, big);
-                    if (nrot) {
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-#pragma unroll
-                            for (int t = 0; t < EPL; ++t) {
-                                if (t < ylanes) {
-                                    rowA[(size_t)i * LS + 32 * t] = v[i][t];
-                                    rowB[(size_t)i * LS + 32 * t] = v[4 + i][t];
-                                }
-                            }
-                        }
-                        float am = a[0];
-#pragma unroll
-                        for (int i = 1; i < 8; ++i) if (lane == i) am = a[i];
-                        if (lane < 8) nrm[lane < 4 ? 4 * I + lane : 4 * Jb + lane - 4] = am;
-                    }
-                    if (r + 1 < nrounds) {
-                        const bool has_r = g + 1 < ngroups, has_l = g > 0;
-                        if (g & 1) {
-                            if (has_l) named_barrier_sync(g, 64);
-                            if (has_r) named_barrier_sync(g + 1, 64);
-                        } else {
-                            if (has_r) named_barrier_sync(g + 1, 64);
-                            if (has_l) named_barrier_sync(g, 64);
-                        }
-                    }
-                }
-            }
-            sweeps = sweep + 1;
-            if (!__syncthreads_or(big ? 1 : 0)) { status = 0; break; }
-        }
+        if (P.LC == 128) jacobi_sweeps<2>(Ys, LS, nrm, nb, P.max_sweeps, P.tol2, sweeps, status);
+        else jacobi_sweeps<1>(Ys, LS, nrm, nb, P.max_sweeps, P.tol2, sweeps, status);
     }
+    const int W = P.LC;                            // rows < 4 nb are planar from here on (the others are zero)
+    const int nplanar = nact >= 2 ? 4 * nb : 0;
 
     PHASE_MARK(3);
     // ---- step 3: singular values, stable descending sort --------------------------------------
     __syncthreads();
     for (int i = warp; i < nvp; i += NW) {
         float s2 = 0.f;
-        if (i < nv) {
+        if (i < nv && i < nplanar) {
+            const float* yr = reinterpret_cast<const float*>(Ys + (size_t)i * LS);
+            for (int c = lane; c < L; c += 32) s2 = fmaf(yr[c], yr[c], fmaf(yr[W + c], yr[W + c], s2));
+        } else if (i < nv) {
             const cf* yr = Ys + (size_t)i * LS;
             for (int c = lane; c < L; c += 32) s2 += cf_abs2(yr[c]);
         }
@@ -670,7 +770,13 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
 #pragma unroll
                 for (int jj = 0; jj < 8; ++jj) {
                     if (jj < njj) {
-                        const cf yb = Ys[(size_t)pj[jj] * LS + c0 + cc];
+                        cf yb;
+                        if (pj[jj] < nplanar) {
+                            const float* yr = reinterpret_cast<const float*>(Ys + (size_t)pj[jj] * LS);
+                            yb = cf_make(yr[c0 + cc], yr[W + c0 + cc]);
+                        } else {
+                            yb = Ys[(size_t)pj[jj] * LS + c0 + cc];
+                        }
 #pragma unroll
                         for (int i = 0; i < 4; ++i) acc[i][jj] = cf_fma_conja(yb, xa[i], acc[i][jj]);   // x conj(y)
                     }
@@ -715,6 +821,7 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
             for (int ci = 0; ci < 4; ++ci) acc[jj][ci] = cf_make(0.f, 0.f);
         const int njj = warp < k ? (k - warp + NW - 1) / NW : 0;
         const int XLS = P.LC + 4;
+        const int ylanes = P.LC / 32;
         for (int a0 = 0; a0 < nv; a0 += XCH) {
             const int ah = min(XCH, nv - a0);
             for (int e = tid; e < ah * P.LC; e += ST) {
@@ -769,7 +876,7 @@ struct Layout { int nvp, LC, LS; size_t smem; };
 Layout make_layout(int nv, int L) {
     Layout lo;
     lo.nvp = (nv + 7) / 8 * 8;
-    lo.LC = (L + 31) / 32 * 32;
+    lo.LC = L <= 64 ? 64 : 128;  // row width of the planar sweep layout (lanes cover 2 or 4 columns)
     lo.LS = lo.LC + 4;           // rows 16-byte aligned; 4 consecutive rows x 4 columns hit 16 distinct 8-byte banks
     lo.smem = ((size_t)lo.nvp * lo.LS + XS_ELEMS + 2 * (size_t)VB + lo.nvp) * 8 + (size_t)lo.nvp * 16 + NW * 4 + 64;
     return lo;

@@ -48,6 +48,30 @@ class SVDNotConverged(RuntimeWarning):
     values may differ from the reference's LAPACK SVD by more than the parity bound."""
 
 
+class _Staging:
+    """One pinned host buffer and its device twin.  A compiled plan's descriptor tables and gate table
+    live in ONE such pair and go to the device in ONE asynchronous copy: the first version allocated
+    and pinned a fresh gate buffer and made two blocking pageable uploads per compile, which serialised
+    host and device on every ``apply_two_qudit_gate`` call."""
+
+    def __init__(self, nbytes: int, device: Any) -> None:
+        torch = _torch()
+        self.cap = int(nbytes)
+        self.host = torch.zeros(self.cap, dtype=torch.uint8).pin_memory()
+        self.dev = torch.empty(self.cap, dtype=torch.uint8, device=device)
+        self.event = None            # recorded after the last run() that read this slot
+
+    def wait(self) -> None:
+        if self.event is not None:
+            self.event.synchronize()
+            self.event = None
+
+
+#: small plans (gate-by-gate use of the API) draw their staging from a ring of reusable slots
+_RING_SLOTS = 32
+_RING_SLOT_BYTES = 64 * 1024
+
+
 class CompiledPlan:
     """A plan bound to a chain's buffers: device descriptor tables + the launch list."""
 
@@ -57,8 +81,10 @@ class CompiledPlan:
         self.launches: List[Tuple] = []
         self.desc1 = None
         self.desc2 = None
-        self.gates = None            # device [ngates][nb_g][width] complex64
-        self.gates_host = None       # pinned staging of the same shape
+        self.staging = None          # _Staging holding desc1 | desc2 | gates
+        self.gates_span = (0, 0)     # byte range of the gate table inside the staging buffers
+        self.gates = None            # device view [ngates][nb_g][width] complex64
+        self.gates_host = None       # pinned view of the same shape
         self.info = None             # device int32 [napps2 * B][2]
         self.svals = None            # device float32 [napps2][B][maxmn] or None
         self.svals_width = 0
@@ -85,6 +111,8 @@ class DeviceChain:
             self.caps[0] = self.caps[-1] = 1
         self._layout_gen = 0
         self._status_flags = []          # device scalars: max SVD status of every run() since the last check
+        self._ring: List[_Staging] = []
+        self._ring_next = 0
         with torch.cuda.device(self.device):
             self._alloc(self.caps)
             self._workspace = None
@@ -163,6 +191,7 @@ class DeviceChain:
         new._workspace = None
         new._layout_gen = 0
         new._status_flags = list(self._status_flags)
+        new._ring, new._ring_next = [], 0
         return new
 
     @_on_device
@@ -176,6 +205,7 @@ class DeviceChain:
         new._workspace = None
         new._layout_gen = 0
         new._status_flags = []
+        new._ring, new._ring_next = [], 0
         return new
 
     def _site_refs(self) -> np.ndarray:
@@ -183,6 +213,19 @@ class DeviceChain:
         for i in range(self.n):
             refs[i] = (self.site_ptr(i), self.total, self.bonds[i], self.bonds[i + 1])
         return refs
+
+    def _staging(self, nbytes: int) -> _Staging:
+        """Staging for a plan: a slot of the ring for small plans (waits for the slot's previous user
+        only when 32 later plans are already in flight), a buffer of its own for a large one."""
+        if nbytes > _RING_SLOT_BYTES:
+            return _Staging(nbytes, self.device)
+        if len(self._ring) < _RING_SLOTS:
+            self._ring.append(_Staging(_RING_SLOT_BYTES, self.device))
+            return self._ring[-1]
+        slot = self._ring[self._ring_next]
+        self._ring_next = (self._ring_next + 1) % _RING_SLOTS
+        slot.wait()
+        return slot
 
     def workspace(self, nbytes: int):
         torch = _torch()
@@ -194,8 +237,11 @@ class DeviceChain:
 
     # ------------------------------------------------------------------ plan compilation
     @_on_device
-    def compile(self, plan: Plan, per_batch_gates: bool = False, record_svals: bool = False) -> CompiledPlan:
-        """Bind ``plan`` (made against the chain's current bonds) to this chain's buffers."""
+    def compile(self, plan: Plan, per_batch_gates: bool = False, record_svals: bool = False,
+                transient: bool = False) -> CompiledPlan:
+        """Bind ``plan`` (made against the chain's current bonds) to this chain's buffers.
+        ``transient``: the plan is run once, right away (gate-by-gate use of the API): its staging may
+        come from the chain's ring of reusable slots instead of a buffer of its own."""
         torch = _torch()
         lib = _lib.load(require_device=True)
         assert plan.bonds_in == self.bonds, "plan was made for different bond dimensions"
@@ -207,16 +253,25 @@ class DeviceChain:
         width = d ** 4
         nb_g = B if per_batch_gates else 1
         ng = len(plan.gates)
-        cp.gates = torch.zeros((max(ng, 1), nb_g, width), dtype=torch.complex64, device=self.device)
-        cp.gates_host = torch.zeros((max(ng, 1), nb_g, width), dtype=torch.complex64).pin_memory()
+        layers = plan.layers()
+        n1, n2 = len(plan.apps1), len(plan.apps2)
+        # one staging pair: [desc1 | desc2 | gates], every part 128-byte aligned
+        b1 = (max(n1, 1) * _lib.GATE1_DESC.itemsize + 127) // 128 * 128
+        b2 = (max(n2, 1) * _lib.GATE2_DESC.itemsize + 127) // 128 * 128
+        bg = max(ng, 1) * nb_g * width * 8
+        st = self._staging(b1 + b2 + bg) if transient else _Staging(b1 + b2 + bg, self.device)
+        cp.staging = st
+        cp.gates_span = (b1 + b2, b1 + b2 + bg)
+        shape = (max(ng, 1), nb_g, width)
+        cp.gates = st.dev[b1 + b2: b1 + b2 + bg].view(torch.complex64).view(shape)
+        cp.gates_host = st.host[b1 + b2: b1 + b2 + bg].view(torch.complex64).view(shape)
         gbase = cp.gates.data_ptr()
         gstride = nb_g * width * 8
         bs_gate = width if per_batch_gates else 0
-
-        layers = plan.layers()
-        n1, n2 = len(plan.apps1), len(plan.apps2)
-        d1 = np.zeros(max(n1, 1), dtype=_lib.GATE1_DESC)
-        d2 = np.zeros(max(n2, 1), dtype=_lib.GATE2_DESC)
+        d1 = st.host[:max(n1, 1) * _lib.GATE1_DESC.itemsize].numpy().view(_lib.GATE1_DESC)
+        d2 = st.host[b1: b1 + max(n2, 1) * _lib.GATE2_DESC.itemsize].numpy().view(_lib.GATE2_DESC)
+        d1[:] = np.zeros(1, dtype=_lib.GATE1_DESC)[0]
+        d2[:] = np.zeros(1, dtype=_lib.GATE2_DESC)[0]
         maxmn = max([min(d * a.chiL, d * a.chiR) for a in plan.apps2] + [1])
         if record_svals and n2:
             cp.svals = torch.zeros((n2, B, maxmn), dtype=torch.float32, device=self.device)
@@ -270,8 +325,8 @@ class DeviceChain:
                 for idx in idxs:
                     a = plan.apps2[idx]
                     bonds[a.site + 1] = a.k
-        cp.desc1 = _lib.to_device_bytes(d1, self.device)
-        cp.desc2 = _lib.to_device_bytes(d2, self.device)
+        cp.desc1 = st.dev[:b1]
+        cp.desc2 = st.dev[b1: b1 + b2]
         # group tables of the layer calls (host arrays; pointers into the uploaded descriptor table)
         p2base, pibase = cp.desc2.data_ptr(), cp.info.data_ptr()
         for li, L in enumerate(launches):
@@ -289,13 +344,18 @@ class DeviceChain:
         cp.owner = self
         # stage the gates of the plan itself (callers may overwrite cp.gates_host and re-upload)
         tab = plan.gate_table(width)
+        cp.gates_host.zero_()
         if ng:
             cp.gates_host[:ng] = torch.from_numpy(tab).unsqueeze(1)
+        # descriptor tables (and these gates) to the device: one asynchronous copy, stream ordered
+        # before every launch of run()
+        st.dev[:b1 + b2].copy_(st.host[:b1 + b2], non_blocking=True)
         return cp
 
     @_on_device
     def upload_gates(self, cp: CompiledPlan) -> None:
-        cp.gates.copy_(cp.gates_host, non_blocking=True)
+        lo, hi = cp.gates_span
+        cp.staging.dev[lo:hi].copy_(cp.staging.host[lo:hi], non_blocking=True)
 
     @_on_device
     def run(self, cp: CompiledPlan, upload: bool = True) -> None:
@@ -328,6 +388,10 @@ class DeviceChain:
                            "mpsb_apply_gate2")
         cp.n_launch_calls = len(cp.launches)
         self.bonds = list(cp.bonds_out)
+        if cp.staging is not None and cp.staging.cap == _RING_SLOT_BYTES:
+            ev = _torch().cuda.Event()
+            ev.record()
+            cp.staging.event = ev        # the ring slot may be rewritten once this run has consumed it
         if cp.plan.apps2:
             self._status_flags.append(cp.info[: len(cp.plan.apps2) * B, 0].max())
             if len(self._status_flags) >= 256:

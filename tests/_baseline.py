@@ -63,14 +63,14 @@ class Baseline:
                                                     if "reference_complex64_sigma_deviation" in z.files else None)
 
 
-def sigma_errors(svals, k, ref):
+def sigma_errors(svals, k, ref, floor=1e-3):
     """(error relative to the largest singular value, worst per-value relative error over the
-    KEPT values >= 1e-3 sigma_max) of one application."""
+    KEPT values >= floor * sigma_max) of one application."""
     ref = np.asarray(ref, dtype=np.float64)
     got = np.asarray(svals, dtype=np.float64)[: ref.size]
     smax = max(ref.max(), 1e-300)
     e_max = np.abs(got - ref).max() / smax
-    sel = ref[:k] >= 1e-3 * smax
+    sel = ref[:k] >= floor * smax
     e_rel = (np.abs(got[:k] - ref[:k])[sel] / ref[:k][sel]).max() if sel.any() else 0.0
     return float(e_max), float(e_rel)
 

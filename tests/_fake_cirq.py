@@ -64,3 +64,42 @@ def Toffoli(a, b, c):
     u = np.eye(8, dtype=complex)
     u[6:, 6:] = [[0, 1], [1, 0]]
     return Op((a, b, c), u)
+
+
+# ---- the gate domain of mpsim/mpsim_cirq/simulator_test.py:279-292 and a random-circuit generator in the
+# ---- spirit of cirq.testing.random_circuit (moments of operations on disjoint, randomly chosen qubits)
+_X = np.array([[0, 1], [1, 0]], dtype=complex)
+_Y = np.array([[0, -1j], [1j, 0]], dtype=complex)
+_Z = np.diag([1, -1]).astype(complex)
+_S = np.diag([1, 1j]).astype(complex)
+_T = np.diag([1, np.exp(0.25j * np.pi)]).astype(complex)
+_CZ = np.diag([1, 1, 1, -1]).astype(complex)
+_SWAP = np.array([[1, 0, 0, 0], [0, 0, 1, 0], [0, 1, 0, 0], [0, 0, 0, 1]], dtype=complex)
+_ISWAP = np.array([[1, 0, 0, 0], [0, 0, 1j, 0], [0, 1j, 0, 0], [0, 0, 0, 1]], dtype=complex)
+
+
+def _fsim(theta, phi):
+    c, s = np.cos(theta), np.sin(theta)
+    return np.array([[1, 0, 0, 0], [0, c, -1j * s, 0], [0, -1j * s, c, 0], [0, 0, 0, np.exp(-1j * phi)]], dtype=complex)
+
+
+GATE_DOMAIN = [(_X, 1), (_Y, 1), (_Z, 1), (_H.astype(complex), 1), (_S, 1), (_T, 1),
+               (_CNOT, 2), (_CZ, 2), (_SWAP, 2), (_CZ, 2), (_ISWAP, 2), (_fsim(0.2, 0.3), 2)]
+
+
+def random_circuit(nqubits, n_moments, op_density, rng):
+    """Every moment: shuffle the qubits, then place gates drawn from GATE_DOMAIN on consecutive free
+    qubits of that order with probability ``op_density`` each (two-qubit gates therefore act on
+    arbitrary, mostly non-adjacent pairs).  Every qubit is touched at least once."""
+    ops = []
+    for _ in range(n_moments):
+        free = list(rng.permutation(nqubits))
+        while free:
+            u, nq = GATE_DOMAIN[rng.randint(len(GATE_DOMAIN))]
+            if nq > len(free):
+                u, nq = GATE_DOMAIN[rng.randint(6)]
+            qs = [free.pop() for _ in range(nq)]
+            if rng.rand() < op_density:
+                ops.append(Op(tuple(int(q) for q in qs), u))
+    ops += [Op((q,), np.eye(2, dtype=complex)) for q in range(nqubits)]
+    return Circuit(ops)

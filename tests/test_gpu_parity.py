@@ -247,21 +247,26 @@ def test_brickwork_vs_oracle(n, depth, chi, seed):
     ora = OracleMPS(n, dtype=np.complex128)
     for op in ops:
         ora.apply_two_qudit_gate(op.tensor, *op.indices, keep_left_canonical=op.keep_left_canonical, **kw)
-    # (a) gate by gate, recording singular values (free running)
+    # (a) gate by gate with the SAME input on both sides (teacher-forced: the two sites a gate touches are
+    # set to the oracle's before it is applied): every singular value of every application within 1e-5
+    # of the application's largest, on the single-CTA path (d*chi <= 128) and on the block-Jacobi path
     mps = mp.MPS(n); mps.record_singular_values(True)
-    svs = []
+    tf = OracleMPS(n, dtype=np.complex128)
     for op in ops:
+        for s_ in op.indices:
+            mps._chain.set_site(s_, tf.sites[s_])
+        tf.apply_two_qudit_gate(op.tensor, *op.indices, keep_left_canonical=op.keep_left_canonical, **kw)
         mps.apply_two_qudit_gate(mp.Node(op.tensor), *op.indices, keep_left_canonical=op.keep_left_canonical, **kw)
-        svs += mps.last_singular_values()
-    assert mps.bond_dimensions() == ora.bond_dimensions()
-    # free-running comparison: per-application errors compound over the depth of the circuit.
-    # The single-CTA path (d*chi <= 128) holds 1e-5 even so; the block-Jacobi path (d*chi > 128)
-    # meets 1e-5 per application (teacher-forced, tests/test_gpu_kernels.py) and 5e-5 free-running.
-    sv_tol = SV_TOL if (chi is None or 2 * chi <= 128) else float(__import__('os').environ.get('MPSB_TEST_LARGE_TOL', 5)) * SV_TOL
-    for s, t in zip(svs, ora.trace):
+        (s,), t = mps.last_singular_values(), tf.trace[-1]
         assert s["k"] == t["k"]
         ref = np.concatenate([t["s_kept"], t["s_trunc"]])
-        assert np.abs(s["svals"] - ref).max() <= sv_tol * ref.max()
+        assert np.abs(s["svals"] - ref).max() <= SV_TOL * ref.max()
+    assert mps.bond_dimensions() == ora.bond_dimensions()
+    # free running (nothing reset in between): state, norm and amplitudes
+    mps = mp.MPS(n)
+    for op in ops:
+        mps.apply_two_qudit_gate(mp.Node(op.tensor), *op.indices, keep_left_canonical=op.keep_left_canonical, **kw)
+    assert mps.bond_dimensions() == ora.bond_dimensions()
     assert abs(mps.norm() - ora.norm()) < 1e-4
     wf, wref = mps.wavefunction(), ora.wavefunction()
     np.testing.assert_allclose(wf, wref, atol=AMP_TOL)
@@ -337,6 +342,38 @@ def test_simulator_ghz_qft_and_sweep():                     # simulator_test.py:
         MPSimulator().simulate(Circuit([H(0)]))                                     # one qubit: simulator_test.py:16-19
     with pytest.raises(ValueError):
         MPSimulator().simulate("not a circuit")
+
+
+@pytest.mark.parametrize("nqubits", [2, 4, 8])
+def test_simulator_random_circuits(nqubits):                # simulator_test.py:274-305
+    """50 random circuits of 25 moments over the reference's gate domain (X, Y, Z, H, S, T, CNOT, CZ, SWAP,
+    CZPow, ISWAP, FSim(0.2, 0.3)) on random -- mostly non-adjacent -- qubit pairs, through MPSimulator,
+    against a dense state-vector simulation (standing in for circuit.final_wavefunction())."""
+    from mpsim_b200.mpsim_cirq import MPSimulator
+    from tests._fake_cirq import random_circuit
+    rng = np.random.RandomState(1)
+    for _ in range(50):
+        circ = random_circuit(nqubits, 25, 0.999, rng)
+        dense = DenseState(nqubits)
+        for op in circ.all_operations():
+            dense.apply(np.asarray(op._unitary_()).reshape((2,) * (2 * len(op.qubits))), op.qubits)
+        wf = MPSimulator().simulate(circ).wavefunction()
+        np.testing.assert_allclose(wf, dense.wavefunction(), atol=2e-5)
+
+
+def test_simulator_custom_gate_and_sweep_of_50():           # simulator_test.py:308-357
+    from mpsim_b200.mpsim_cirq import MPSimulator
+    from mpsim_b200.gates import haar_random_unitary_tensor
+    from tests._fake_cirq import Circuit, Op, Rx
+    u = haar_random_unitary_tensor(2, 2, rng=np.random.RandomState(1)).reshape(4, 4)
+    wf = MPSimulator().simulate(Circuit([Op((0, 1), u)])).wavefunction()
+    np.testing.assert_allclose(wf, u[:, 0], atol=1e-6)
+    params = [{"theta": t} for t in np.linspace(0, 2 * np.pi, 50)]
+    allmps = MPSimulator().simulate_sweep(Circuit([Rx("theta", 0), Rx("theta", 1)]), params)
+    assert len(allmps) == 50
+    for pr, mps in zip(params, allmps):
+        c, s_ = np.cos(pr["theta"] / 2), -1j * np.sin(pr["theta"] / 2)
+        np.testing.assert_allclose(mps.wavefunction(), np.kron([c, s_], [c, s_]), atol=1e-6)
 
 
 def test_simulator_batched_sweep_matches_sequential():          # simulator.py:67-87 as ONE batched run
