@@ -362,14 +362,47 @@ int mpsb_scale_sites(const mpsb_site_ref* sites_dev, int nsites, int nbatch, int
     return launch_scale(sites_dev, nsites, nbatch, d, factors_dev, max_site_elems, (cudaStream_t)stream);
 }
 
-size_t mpsb_wavefunction_workspace_bytes(const mpsb_site_ref* s, int nsites, int d) {
-    size_t rows = 1, mx = 1;
-    for (int i = 0; i < nsites; ++i) {
-        rows *= (size_t)d;
-        size_t e = rows * (size_t)(s[i].chiR > 0 ? s[i].chiR : 1);
-        if (e > mx) mx = e;
+// Dense wavefunction of one chain: contracted from BOTH ends and joined by one product,
+//   L [d^sp][chi_sp]   = A_0 A_1 ... A_{sp-1}          (left chain, rows = leading digits)
+//   R [chi_sp][d^(n-sp)] = A_sp ... A_{n-1}            (right chain, columns = trailing digits)
+//   psi [d^sp][d^(n-sp)] = L . R                        (big-endian index, mpsim/core.py:483-500)
+// A one-sided chain materialises d^(i+1) x chi_{i+1} partial products all the way to the last site --
+// 16 x the output at n = 24, chi = 64 (the right end of a chain has bonds 64, 32, ..., 2, 1 while the row
+// count keeps doubling) -- and ran at 25 GB/s of output (bench.py, round 2); split at the site that
+// minimises the bytes of all partial products, the products are ~2 x the output and the join is one GEMM
+// with K = chi_sp (on the tcgen05 kernel when the tile fills).
+struct WfPlan { int sp; size_t maxL, maxR, tc_floats; bool tc; };
+
+static WfPlan wf_plan(const mpsb_site_ref* s, int n, int d) {
+    std::vector<double> Ls(n), Rs(n);          // elements of L after site i, of R from site i
+    double rows = 1;
+    for (int i = 0; i < n; ++i) { rows *= d; Ls[i] = rows * (s[i].chiR > 0 ? s[i].chiR : 1); }
+    double cols = 1;
+    for (int i = n - 1; i >= 0; --i) { cols *= d; Rs[i] = cols * (s[i].chiL > 0 ? s[i].chiL : 1); }
+    WfPlan p; p.sp = 1;
+    double best = -1;
+    for (int sp = 1; sp <= n - 1; ++sp) {
+        double tot = 0;
+        for (int i = 1; i < sp; ++i) tot += Ls[i];           // site 0 is used in place
+        for (int i = sp; i < n - 1; ++i) tot += Rs[i];       // the last site is used in place
+        if (best < 0 || tot < best) { best = tot; p.sp = sp; }
     }
-    return 2 * align_up(mx, 16) * sizeof(cf) + 256;
+    p.maxL = 1; p.maxR = 1;
+    for (int i = 1; i < p.sp; ++i) if ((size_t)Ls[i] > p.maxL) p.maxL = (size_t)Ls[i];
+    for (int i = p.sp; i < n - 1; ++i) if ((size_t)Rs[i] > p.maxR) p.maxR = (size_t)Rs[i];
+    double M = 1, N = 1;
+    for (int i = 0; i < p.sp; ++i) M *= d;
+    for (int i = p.sp; i < n; ++i) N *= d;
+    const int K = s[p.sp].chiL;
+    p.tc = K >= 16 && M >= 256 && N >= 128 && M <= 0x7fffffff && N <= 0x7fffffff;
+    p.tc_floats = p.tc ? tc_cgemm_workspace_floats(1, (int)M, (int)N, K) : 0;
+    return p;
+}
+
+size_t mpsb_wavefunction_workspace_bytes(const mpsb_site_ref* s, int nsites, int d) {
+    if (!s || nsites < 2) return 256;
+    const WfPlan p = wf_plan(s, nsites, d);
+    return (2 * align_up(p.maxL, 16) + 2 * align_up(p.maxR, 16)) * sizeof(cf) + align_up(p.tc_floats * sizeof(float), 256) + 512;
 }
 
 int mpsb_wavefunction(const mpsb_site_ref* s, int nsites, int d, int batch_index,
@@ -378,6 +411,7 @@ int mpsb_wavefunction(const mpsb_site_ref* s, int nsites, int d, int batch_index
     MPSB_ARG(s && nsites >= 2 && out, "wavefunction: bad arguments");
     MPSB_ARG(s[0].chiL == 1 && s[nsites - 1].chiR == 1, "wavefunction: chain ends must have bond dimension 1");
     MPSB_ARG(workspace_bytes >= mpsb_wavefunction_workspace_bytes(s, nsites, d), "wavefunction: workspace too small");
+    MPSB_ARG(((uintptr_t)workspace & 255) == 0, "wavefunction: workspace must be 256-byte aligned");
     size_t total = 1;
     bool empty = false;
     for (int i = 0; i < nsites; ++i) {
@@ -389,22 +423,43 @@ int mpsb_wavefunction(const mpsb_site_ref* s, int nsites, int d, int batch_index
         MPSB_CUDA(cudaMemsetAsync(out, 0, total * sizeof(cf), st));
         return 0;
     }
-    size_t half = (workspace_bytes - 256) / 2 / sizeof(cf) / 16 * 16;
-    cf* buf[2] = {(cf*)workspace, (cf*)workspace + half};
-    const cf* cur = (const cf*)s[0].site + (int64_t)batch_index * s[0].bs;    // [d][chi1]
+    const WfPlan p = wf_plan(s, nsites, d);
+    cf* w = (cf*)workspace;
+    cf* Lb[2] = {w, w + align_up(p.maxL, 16)};
+    w += 2 * align_up(p.maxL, 16);
+    cf* Rb[2] = {w, w + align_up(p.maxR, 16)};
+    w += 2 * align_up(p.maxR, 16);
+    float* tcw = (float*)(((uintptr_t)w + 255) & ~(uintptr_t)255);
+    auto site = [&](int i) { return (const cf*)s[i].site + (int64_t)batch_index * s[i].bs; };
+    // left chain: L_i [d^(i+1)][chi_{i+1}] = L_{i-1} [d^i][chi_i] . A_i [chi_i][d chi_{i+1}]
+    const cf* L = site(0);
     size_t rows = d;
-    for (int i = 1; i < nsites; ++i) {
-        cf* dst = (i == nsites - 1) ? (cf*)out : buf[i & 1];
-        int chi = s[i].chiL, chi2 = s[i].chiR;
+    for (int i = 1; i < p.sp; ++i) {
         MPSB_ARG(rows <= 0x7fffffff, "wavefunction: too many qudits");
-        int rc = launch_cgemm(cur, chi, 1, 0, 0,
-                              (const cf*)s[i].site + (int64_t)batch_index * s[i].bs, (int64_t)d * chi2, 1, 0, 0,
-                              dst, (int64_t)d * chi2, 0, (int)rows, d * chi2, chi, 1, st);
+        cf* dst = Lb[i & 1];
+        int rc = launch_cgemm(L, s[i].chiL, 1, 0, 0, site(i), (int64_t)d * s[i].chiR, 1, 0, 0,
+                              dst, (int64_t)d * s[i].chiR, 0, (int)rows, d * s[i].chiR, s[i].chiL, 1, st);
         if (rc) return rc;
-        cur = dst;
+        L = dst;
         rows *= (size_t)d;
     }
-    return 0;
+    // right chain: R_i [chi_i][d cols] = A_i [(chi_i, d)][chi_{i+1}] . R_{i+1} [chi_{i+1}][cols]
+    const cf* R = site(nsites - 1);
+    size_t cols = d;
+    for (int i = nsites - 2; i >= p.sp; --i) {
+        MPSB_ARG(cols <= 0x7fffffff, "wavefunction: too many qudits");
+        cf* dst = Rb[i & 1];
+        int rc = launch_cgemm(site(i), s[i].chiR, 1, 0, 0, R, (int64_t)cols, 1, 0, 0,
+                              dst, (int64_t)cols, 0, s[i].chiL * d, (int)cols, s[i].chiR, 1, st);
+        if (rc) return rc;
+        R = dst;
+        cols *= (size_t)d;
+    }
+    MPSB_ARG(rows <= 0x7fffffff && cols <= 0x7fffffff, "wavefunction: too many qudits");
+    const int K = s[p.sp].chiL;
+    if (p.tc)
+        return launch_cgemm_tc(L, 0, R, 0, (cf*)out, (int64_t)cols, 0, (int)rows, (int)cols, K, 1, tcw, st);
+    return launch_cgemm(L, K, 1, 0, 0, R, (int64_t)cols, 1, 0, 0, (cf*)out, (int64_t)cols, 0, (int)rows, (int)cols, K, 1, st);
 }
 
 int mpsb_amplitudes(const mpsb_site_ref* sites_dev, int nsites, int nbatch, int d, int max_chi,

@@ -20,7 +20,7 @@ cgemm_kernel(const cf* __restrict__ A, int64_t a_rs, int64_t a_cs, int64_t a_bs,
     __shared__ cf Bs[BK][BN + 1];
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;       // 16 x 16 threads, 4 x 4 outputs each
-    const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+    const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;      // M on grid.x: tall-skinny products (wavefunction chain) are not capped at 65 535 tiles
     A += (int64_t)blockIdx.z * a_bs;
     B += (int64_t)blockIdx.z * b_bs;
     C += (int64_t)blockIdx.z * c_bs;
@@ -92,8 +92,8 @@ int launch_cgemm(const cf* A, int64_t a_rs, int64_t a_cs, int conj_a, int64_t a_
                  cf* C, int64_t c_ld, int64_t c_bs, int M, int N, int K, int nbatch,
                  cudaStream_t st) {
     if (M <= 0 || N <= 0 || nbatch <= 0) return 0;
-    dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM, nbatch);
-    MPSB_ARG(grid.y <= 65535 && grid.z <= 65535, "cgemm: grid too large (M=%d, nbatch=%d)", M, nbatch);
+    dim3 grid((M + BM - 1) / BM, (N + BN - 1) / BN, nbatch);
+    MPSB_ARG(grid.y <= 65535 && grid.z <= 65535, "cgemm: grid too large (N=%d, nbatch=%d)", N, nbatch);
 #define GO(CA, CB) cgemm_kernel<CA, CB><<<grid, GT, 0, st>>>(A, a_rs, a_cs, a_bs, B, b_rs, b_cs, b_bs, C, c_ld, c_bs, M, N, K)
     if (conj_a && conj_b) GO(true, true);
     else if (conj_a) GO(true, false);

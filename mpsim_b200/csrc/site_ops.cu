@@ -137,7 +137,8 @@ int launch_gate1(const mpsb_gate1_desc* descs, int ndesc, int nbatch, int d, int
         case 2: gate1_kernel<2><<<grid, 256, 0, st>>>(descs, nbatch); break;
         case 3: gate1_kernel<3><<<grid, 256, 0, st>>>(descs, nbatch); break;
         case 4: gate1_kernel<4><<<grid, 256, 0, st>>>(descs, nbatch); break;
-        default: MPSB_ARG(false, "gate1: qudit dimension %d not supported on device (2..4)", d);
+        case 5: gate1_kernel<5><<<grid, 256, 0, st>>>(descs, nbatch); break;
+        default: MPSB_ARG(false, "gate1: qudit dimension %d not supported on device (2..5)", d);
     }
     MPSB_LAUNCH_CHECK("gate1_kernel");
     return 0;

@@ -664,18 +664,10 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
 
     PHASE_MARK(1);
     // ---- step 1: Householder QR, R only ------------------------------------------------------
-    // In panels of 32 steps on the shrinking trailing matrix: a thread owns a fixed column slice for a
-    // whole call, so in one call over all 127 steps the owners of finished columns idle (half of the
-    // threads on average); every new call spreads the remaining columns over all 512 threads again
-    // (threads per column 4 -> 4 -> 8 -> 16).
-    if (P.do_qr) {
-        const int nsteps = min(nv - 1, L);
-        for (int j0 = 0; j0 < nsteps;) {
-            const int chunk = nsteps - j0 > 48 ? 32 : nsteps - j0;
-            householder<0>(Ys + (size_t)j0 * LS + j0, LS, nv - j0, L - j0, chunk, vbuf, scal, nullptr, nullptr);
-            j0 += chunk;
-        }
-    }
+    // (Measured and not adopted: the factorisation in panels of 32 steps on the shrinking trailing matrix,
+    // so that the owners of finished columns do not idle -- 540 k -> 563 k cycles: a step is bound by its
+    // ~2 000-cycle scalar / publish / barrier chain, not by the column update.)
+    if (P.do_qr) householder<0>(Ys, LS, nv, L, min(nv - 1, L), vbuf, scal, nullptr, nullptr);
 
     PHASE_MARK(2);
     // ---- step 2: one-sided Jacobi on the rows of Y -------------------------------------------

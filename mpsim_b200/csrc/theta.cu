@@ -137,7 +137,8 @@ int launch_theta(const mpsb_gate2_desc* descs, int ndesc, int nbatch, int d, int
     switch (d) {
         case 2: theta_kernel<2><<<grid, TT, 0, st>>>(descs, nbatch, chiL, chiM, chiR, transpose_out, out, out_job_stride); break;
         case 3: theta_kernel<3><<<grid, TT, 0, st>>>(descs, nbatch, chiL, chiM, chiR, transpose_out, out, out_job_stride); break;
-        default: MPSB_ARG(false, "theta: qudit dimension %d not supported on device (2 or 3)", d);
+        case 4: theta_kernel<4><<<grid, TT, 0, st>>>(descs, nbatch, chiL, chiM, chiR, transpose_out, out, out_job_stride); break;
+        default: MPSB_ARG(false, "theta: qudit dimension %d not supported on device (2..4)", d);
     }
     MPSB_LAUNCH_CHECK("theta_kernel");
     return 0;

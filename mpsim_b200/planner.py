@@ -101,6 +101,9 @@ class Plan:
     def _add_adjacent(self, tensor: np.ndarray, site: int, kwargs: Dict[str, Any], source_op: int,
                       is_swap: bool, flipped: bool = False) -> None:
         d = self.d
+        if d > MAX_DEVICE_QUDIT_DIMENSION:
+            raise ValueError(f"two-qudit gates are implemented on the device for qudit dimension 2..{MAX_DEVICE_QUDIT_DIMENSION} "
+                             f"(theta kernel instantiations), not {d}")
         keep_left, maxsvals = resolve_truncation(kwargs, self.n, d, site)
         chiL, chiM, chiR = self.bonds[site], self.bonds[site + 1], self.bonds[site + 2]
         full = min(d * chiL, d * chiR)
@@ -156,6 +159,9 @@ class Plan:
     def counts(self) -> Dict[str, int]:
         return dict(one_qudit=len(self.apps1), adjacent_applications=len(self.apps2),
                     swaps=sum(a.is_swap for a in self.apps2), layers=self.nlayers)
+
+
+MAX_DEVICE_QUDIT_DIMENSION = 4       # csrc/theta.cu: theta_kernel<2..4>
 
 
 def plan_operations(nqudits: int, d: int, bonds: Sequence[int],

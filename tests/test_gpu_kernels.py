@@ -166,7 +166,7 @@ def test_svd_batch_of_128x128():
 
 
 @pytest.mark.parametrize("chi", [(1, 1, 1), (2, 1, 2), (4, 8, 2), (16, 16, 16), (33, 17, 40), (64, 64, 64)])
-@pytest.mark.parametrize("d", [2, 3])
+@pytest.mark.parametrize("d", [2, 3, 4])
 def test_theta(chi, d):
     import torch
     from mpsim_b200 import _lib

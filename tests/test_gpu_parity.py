@@ -283,6 +283,37 @@ def test_brickwork_vs_oracle(n, depth, chi, seed):
     np.testing.assert_allclose(disp.amplitudes(bits), wref[idx], atol=AMP_TOL)
 
 
+@pytest.mark.parametrize("d", [3, 4])
+def test_qudit_circuit_vs_oracle(d):
+    """Qudit dimensions beyond 2 (the reference is dimension-agnostic, mpsim/core.py:161-166 and its tests build
+    d = 3 ... 5 states): Haar one- and two-qudit gates on adjacent sites in both orders, with and without
+    truncation.  (Non-adjacent gates route through the QUBIT swap gate in the reference, core.py:1376-1380,
+    and fail there for d > 2 -- here too, with the same ValueError.)"""
+    import mpsim_b200 as mp
+    from mpsim_b200.gates import haar_random_unitary_tensor
+    n = 5
+    rng = np.random.RandomState(10 + d)
+    pairs = [(0, 1), (2, 3), (1, 2), (3, 4), (2, 1), (4, 3), (2, 3), (1, 0)]
+    for kw in ({}, {"maxsvals": 2 * d}):
+        mps = mp.MPS(n, qudit_dimension=d)
+        ora = OracleMPS(n, qudit_dimension=d, dtype=np.complex128)
+        for q in range(n):
+            g = haar_random_unitary_tensor(1, d, rng=rng)
+            mps.apply_one_qudit_gate(mp.Node(g), q); ora.apply_one_qudit_gate(g, q)
+        for (a, b) in pairs:
+            g = haar_random_unitary_tensor(2, d, rng=rng)
+            mps.apply_two_qudit_gate(mp.Node(g), a, b, **kw); ora.apply_two_qudit_gate(g, a, b, **kw)
+        assert mps.bond_dimensions() == ora.bond_dimensions()
+        assert abs(mps.norm() - ora.norm()) < 1e-4
+        np.testing.assert_allclose(mps.wavefunction(), ora.wavefunction(), atol=AMP_TOL)
+    with pytest.raises(ValueError):
+        mp.MPS(n, qudit_dimension=d).apply_two_qudit_gate(mp.Node(haar_random_unitary_tensor(2, d, rng=rng)), 0, 3)
+    # two-qudit gates on d > 4 are refused on the host, before anything is launched (one-qudit gates,
+    # from_wavefunction and the observables work for any d)
+    with pytest.raises(ValueError, match="qudit dimension"):
+        mp.MPS(3, qudit_dimension=5).apply_two_qudit_gate(mp.Node(haar_random_unitary_tensor(2, 5, rng=rng)), 0, 1)
+
+
 def test_batch_matches_oracle_per_member():
     import mpsim_b200 as mp
     from mpsim_b200 import circuits
