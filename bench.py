@@ -345,7 +345,15 @@ def time_secondary(torch, args, batch):
                                "note": "one site (chi x 2 x chi) of every batch member: small launch, latency bound"}
     ms = ev(lambda: chain.norms(), reps=3)
     site_bytes = sum(8.0 * chain.site_elems(i) for i in range(chain.n)) * B
-    out["norm_chain"] = {"ms": ms, "launches": 2 * chain.n + 2, "gbs_sites_read_once": site_bytes / (ms * 1e-3) / 1e9}
+    # transfer chain: env <- A^H (env A) per site = 2 x 8 d chiL chiR max(chiL, chiR)-ish flops; exactly
+    # 8 chiL chiL d chiR (env . A) + 8 chiR d chiL chiR (A^H . tmp) real flops per site and member
+    norm_flops = sum(8.0 * chain.bonds[i] * chain.bonds[i] * d * chain.bonds[i + 1]
+                     + 8.0 * chain.bonds[i + 1] * d * chain.bonds[i] * chain.bonds[i + 1] for i in range(chain.n)) * B
+    out["norm_chain"] = {"ms": ms, "launches": 2 * chain.n + 2, "gbs_sites_read_once": site_bytes / (ms * 1e-3) / 1e9,
+                         "tflops": norm_flops / (ms * 1e-3) / 1e12,
+                         "note": "2 x 8 d chi^3 flops against 8 d chi^2 bytes per site: intensity 2 chi = 128 flop/B at "
+                                 "chi = 64, i.e. FFMA bound (cgemm_kernel), not HBM bound; the GB/s figure is what the "
+                                 "north star asks to be reported"}
     # renormalize scale pass (scale_kernel): every site read and written once, 16 d chiL chiR bytes per site
     ones = torch.ones(B, dtype=torch.float32, device=chain.device)
     ms = ev(lambda: chain.scale(ones), reps=3)

@@ -314,6 +314,37 @@ def test_qudit_circuit_vs_oracle(d):
         mp.MPS(3, qudit_dimension=5).apply_two_qudit_gate(mp.Node(haar_random_unitary_tensor(2, 5, rng=rng)), 0, 1)
 
 
+def test_mps_on_a_non_current_device():
+    """An MPS / MPSBatch built on cuda:1 while cuda:0 is current launches on cuda:1's stream against cuda:1's
+    memory (every DeviceChain entry point switches device; the library's stream pool and pinned slots are per
+    device).  Needs two GPUs."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    import mpsim_b200 as mp
+    from mpsim_b200 import circuits
+    torch.cuda.set_device(0)
+    n = 8
+    mps = mp.MPS(n, device="cuda:1")
+    mps.h(0)
+    for i in range(n - 1):
+        mps.cnot(i, i + 1)
+    mps.cnot(0, n - 1)                                       # swap network
+    assert mps._chain.slab.device.index == 1 and torch.cuda.current_device() == 0
+    ghz = np.zeros(2 ** n); ghz[0] = ghz[-2] = 2 ** -0.5     # last CNOT flips the last qubit of |1..1>
+    np.testing.assert_allclose(mps.wavefunction(), ghz, atol=1e-6)
+    assert abs(mps.norm() - 1) < 1e-6
+    # a chi = 96 bond: the block-Jacobi path (library-owned streams and pinned read-back slots of device 1)
+    ops = circuits.brickwork(16, 14, seed=4)
+    big = mp.MPS(16, device="cuda:1")
+    ref = mp.MPS(16, device="cuda:0")
+    for m in (big, ref):
+        m._execute([(o.tensor, o.indices, {"maxsvals": 96, "keep_left_canonical": o.keep_left_canonical}) for o in ops])
+    assert (big.last_status()[:, 0] == 0).all() and big.bond_dimensions() == ref.bond_dimensions()
+    assert abs(big.norm() - ref.norm()) < 1e-4
+    assert torch.cuda.current_device() == 0
+
+
 def test_batch_matches_oracle_per_member():
     import mpsim_b200 as mp
     from mpsim_b200 import circuits
