@@ -676,36 +676,32 @@ __global__ void __launch_bounds__(TA_THREADS, 1) bj_apply_tc_kernel(LargeParams 
 
     if (warp > TA_EPI_WARPS) {
         // ===== loaders: global -> registers (hi/lo split) -> swizzled K-major operands =====
-        // Software pipelined over two register tiles: the 16 loads of the NEXT tile are issued before the
-        // current one is split and stored, so a tile's DRAM latency is covered by the processing of its
-        // predecessor.  (First version: loads, wait, split, store per tile -- one 32 KB tile in flight per SM,
-        // 3.1 TB/s and the tensor pipe 17 % busy in profiles/r2_svd_large_ncu_full.txt.)
         const int lt = threadIdx.x - (TA_EPI_WARPS + 1) * 32, lw = lt >> 5;
-        constexpr int RPW = P / TA_LOAD_WARPS, CPL = TA_M / 32;
         long long held0 = -1, held1 = -1;                  // pair whose B each stage holds
         int n = 0;
-        auto next_item = [&](long long it) {               // first item >= it that is not skipped (or it1)
-            while (it < it1 && ta_item(p, it, ntot).skip) ++it;
-            return it;
-        };
-        auto issue = [&](long long it, cf (&v)[RPW][CPL]) {
+        for (long long it = it0; it < it1; ++it) {
             const TaItem w = ta_item(p, it, ntot);
+            if (w.skip) continue;
+            const int s = n & 1;
+            uint8_t* st = ring + (size_t)s * TA_STAGE_BYTES;
             int I, J;
             pair_blocks(p.nb, round, w.g, I, J);
             const cf* base; int ld, c0, ncol;
             if (w.tile < ntx) { base = p.X + (size_t)w.job * p.x_stride; ld = p.L; c0 = w.tile * TA_M; ncol = p.L; }
             else { base = p.Z + (size_t)w.job * p.z_stride; ld = p.nvp; c0 = (w.tile - ntx) * TA_M; ncol = p.nvp; }
+            // all 16 loads of this thread first (the shared-memory stores below may alias them as far as
+            // the compiler knows: interleaved, every load waited for the previous store -- 8 us per tile).
+            // Measured and not adopted (round 2): a second register tile so that the loads of the NEXT tile
+            // are in flight while this one is split and stored -- 50 x 512^2 145 -> 157 ms, configs[2]
+            // 890 -> 820 applications/s (the loader warps spill at the 128-register cap of a 416-thread CTA).
+            constexpr int RPW = P / TA_LOAD_WARPS, CPL = TA_M / 32;
+            cf v[RPW][CPL];
 #pragma unroll
             for (int rr = 0; rr < RPW; ++rr) {
                 const cf* row = base + (size_t)pair_row(I, J, lw * RPW + rr) * ld + c0;
 #pragma unroll
                 for (int j = 0; j < CPL; ++j) v[rr][j] = c0 + lane + 32 * j < ncol ? __ldcg(row + lane + 32 * j) : cf_make(0.f, 0.f);
             }
-        };
-        auto process = [&](long long it, cf (&v)[RPW][CPL]) {
-            const TaItem w = ta_item(p, it, ntot);
-            const int s = n & 1;
-            uint8_t* st = ring + (size_t)s * TA_STAGE_BYTES;
             const long long pr = (long long)w.job * p.npairs + w.g;
             const bool newq = (s ? held1 : held0) != pr;
             cf qv[P * P / TA_LOAD_THREADS];
@@ -714,7 +710,7 @@ __global__ void __launch_bounds__(TA_THREADS, 1) bj_apply_tc_kernel(LargeParams 
 #pragma unroll
                 for (int j = 0; j < P * P / TA_LOAD_THREADS; ++j) qv[j] = __ldcg(Q + lt + TA_LOAD_THREADS * j);
             }
-            mbar_wait(&empty_bar[s], ((n >> 1) & 1) ^ 1);
+            mbar_wait(&empty_bar[s], ((n >> 1) & 1) ^ 1);    // (the loads above are in flight while the stage drains)
 #pragma unroll
             for (int rr = 0; rr < RPW; ++rr) {
                 const int k = lw * RPW + rr;
@@ -750,18 +746,6 @@ __global__ void __launch_bounds__(TA_THREADS, 1) bj_apply_tc_kernel(LargeParams 
             named_bar_sync(1, TA_LOAD_THREADS);
             if (lt == 0) mbar_arrive(&full_bar[s]);
             ++n;
-        };
-        cf va[RPW][CPL], vb[RPW][CPL];
-        long long ia = next_item(it0);
-        if (ia < it1) issue(ia, va);
-        while (ia < it1) {
-            const long long ib = next_item(ia + 1);
-            if (ib < it1) issue(ib, vb);
-            process(ia, va);
-            if (ib >= it1) break;
-            ia = next_item(ib + 1);
-            if (ia < it1) issue(ia, va);
-            process(ib, vb);
         }
     } else if (warp == TA_EPI_WARPS) {
         // ===== MMA issuer =====

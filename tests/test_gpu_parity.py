@@ -491,3 +491,20 @@ def test_non_unitary_gate_orthonormalizes_and_renormalizes():      # core_test.p
     ora.apply_one_qudit_gate(proj, 1); m.apply_one_qudit_gate(mp.Node(proj), 1)
     assert m.bond_dimensions() == ora.bond_dimensions()
     assert fidelity(m.wavefunction(), ora.wavefunction()) >= 1 - FID_TOL
+    # a GENERIC rank-deficient state: Haar layers, then a projector in the middle of the chain.  The bonds
+    # next to the projected site lose rank; the fp32 SVD returns the numerically zero singular values at
+    # ~1e-7 sigma_max, above the reference's 1e-8 * norm cut, so the cut is clamped to the fp32 noise
+    # floor (ortho.py) -- the bond dimensions must come out as in the complex128 reference
+    from mpsim_b200 import circuits
+    n = 8
+    ops = circuits.brickwork(n, 6, seed=12)
+    ora = OracleMPS(n, dtype=np.complex128); m = mp.MPS(n)
+    for op in ops:
+        ora.apply_two_qudit_gate(op.tensor, *op.indices, keep_left_canonical=op.keep_left_canonical)
+        m.apply_two_qudit_gate(mp.Node(op.tensor), *op.indices, keep_left_canonical=op.keep_left_canonical)
+    for site in (3, 4):
+        ora.apply_one_qudit_gate(proj, site); m.apply_one_qudit_gate(mp.Node(proj), site)
+    assert m.bond_dimensions() == ora.bond_dimensions(), (m.bond_dimensions(), ora.bond_dimensions())
+    assert max(ora.bond_dimensions()) < 16                    # the projectors did reduce the middle bonds
+    assert abs(m.norm() - ora.norm()) < 1e-4
+    assert fidelity(m.wavefunction(), ora.wavefunction()) >= 1 - FID_TOL
