@@ -40,9 +40,10 @@ pytestmark = pytest.mark.gpu
 
 SV_TOL = 1e-5          # relative to sigma_max of the application, and per kept value >= 1e-3 sigma_max
 # FREE-RUNNING bounds (see the module docstring), per fixture: (singular-value trace / sigma_max, norm relative,
-# sampled infidelity, worst sampled amplitude error / rms amplitude).  Measured on B200 (round 2, worst of
-# three runs -- the block-Jacobi path sums its Gram partials in an order that varies from run to run, and a
-# truncated circuit amplifies even that):
+# sampled infidelity, worst sampled amplitude error / rms amplitude).  Measured on B200 (round 2; the runs are
+# deterministic, but any change of the kernels' rounding moves these figures by a small factor -- the swap-network
+# trace was 1.3e-3 before and 4.3e-3 after the sweep engine went to packed FFMA2 -- which is what amplification
+# of rounding differences looks like):
 #                         sigma trace   norm      infidelity   amplitude/rms
 #   config3_member0/511   2.2e-4        4.0e-4    6.7e-5       2.6e-2          (single-CTA path only)
 #   snake_4x4_chi96       4.3e-3        1.0e-4    1.7e-3       1.0e-1
