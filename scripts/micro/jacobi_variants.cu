@@ -589,6 +589,161 @@ __global__ void __launch_bounds__(512, 1) jacobi_v5(const cf* X, cf* Yout, int* 
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// V6: V2 with FAST (scaled) rotations.  Row p is stored as y_p with a log2 scale l_p: true row = 2^l_p y_p.
+// The rotation [c s; -conj(s) c] of the true rows becomes two complex axpys on the stored rows,
+//   y_p <- y_p + alpha y_q,   y_q <- y_q - beta y_p(old),   alpha = (s/c) 2^(l_q - l_p),  beta = conj(s/c) 2^(l_p - l_q),
+// and both scales take the factor c (l += log2 c): 8 FMA per element pair instead of 12.  Gram entries,
+// thresholds, rotation parameters and the running squared norms are those of the TRUE rows.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx_(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+__device__ __forceinline__ void fast_apply_p(float ar, float ai, float br, float bi, Row& p, Row& q) {
+    const float2 AR = make_float2(ar, ar), AI = make_float2(ai, ai), NAI = make_float2(-ai, -ai);
+    const float2 NBR = make_float2(-br, -br), BI = make_float2(bi, bi), NBI = make_float2(-bi, -bi);
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        const float2 pre = p.re[t], pim = p.im[t], qre = q.re[t], qim = q.im[t];
+        p.re[t] = __ffma2_rn(AR, qre, __ffma2_rn(NAI, qim, pre));      // p + alpha q
+        p.im[t] = __ffma2_rn(AR, qim, __ffma2_rn(AI, qre, pim));
+        q.re[t] = __ffma2_rn(NBR, pre, __ffma2_rn(BI, pim, qre));      // q - beta p(old)
+        q.im[t] = __ffma2_rn(NBR, pim, __ffma2_rn(NBI, pre, qim));
+    }
+}
+
+// the squared norms and log2 scales of the rows stay in shared memory (nrm / lsc, indexed by row): the lanes of
+// octet i fetch those of their pair and lane 8 i writes the updated values back (no per-lane copies of all 8)
+template <int A0, int A1, int A2, int A3, int B0, int B1, int B2, int B3>
+__device__ __forceinline__ int sub_round_f4(Row (&y)[8], float* nrm, float* lsc, int rowI, int rowJ, int lane, bool& big) {
+    constexpr int PA[4] = {A0, A1, A2, A3}, PB[4] = {B0, B1, B2, B3};
+    const int sel = lane >> 3;
+    int xa = PA[0], xb = PB[0];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) if (sel == i) { xa = PA[i]; xb = PB[i]; }
+    const int rp = xa < 4 ? rowI + xa : rowJ + xa - 4, rq = xb < 4 ? rowI + xb : rowJ + xb - 4;
+    const float ap = nrm[rp], aq = nrm[rq], lp = lsc[rp], lq = lsc[rq];
+    float gr[4], gi[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gram_part(y[PA[i]], y[PB[i]], gr[i], gi[i]);
+    float mgr = reduce4(gr, lane), mgi = reduce4(gi, lane);
+    const float dd = ex2_approx(lp + lq);
+    mgr *= dd; mgi *= dd;                                      // Gram entry of the true rows
+    const float g2 = fmaf(mgr, mgr, mgi * mgi), apq = ap * aq;
+    float c = 1.f, sr = 0.f, si = 0.f, tg = 0.f;
+    const bool dorot = (g2 > TOL2 * apq) && (g2 > 1e-30f);
+    big = big || (dorot && g2 > BIG2 * apq);
+    float ar = 0.f, ai = 0.f, br = 0.f, bi = 0.f;
+    if (dorot) {
+        rot_params(ap, aq, mgr, mgi, g2, c, sr, si, tg);
+        float ic = rcp_approx_(c);
+        ic = ic * fmaf(-c, ic, 2.0f);                          // Newton: c in [0.707, 1]
+        const float tr = sr * ic, ti = si * ic;                // t = s / c
+        const float eq = ex2_approx(lq - lp), ep = ex2_approx(lp - lq);
+        ar = tr * eq; ai = ti * eq;
+        br = tr * ep; bi = -ti * ep;
+        const float h = fmaf(sr, sr, si * si);                 // c^2 = 1 - h
+        float lc;
+        if (h < 0.0625f) lc = -0.72134752f * h * fmaf(h, fmaf(h, fmaf(h, 0.25f, 0.33333334f), 0.5f), 1.0f);
+        else lc = lg2_approx(c);
+        if ((lane & 7) == 0) {
+            nrm[rp] = fmaxf(ap + tg, 0.f); nrm[rq] = fmaxf(aq - tg, 0.f);
+            lsc[rp] = lp + lc; lsc[rq] = lq + lc;
+        }
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, dorot);
+    const unsigned flags = (bal & 1u) | ((bal >> 7) & 2u) | ((bal >> 14) & 4u) | ((bal >> 21) & 8u);
+    if (flags == 0u) return 0;
+    __syncwarp();                                              // the updates of nrm / lsc are visible to the next sub-round
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        if (flags & (1u << i)) {
+            const float ari = __shfl_sync(0xffffffffu, ar, 8 * i), aii = __shfl_sync(0xffffffffu, ai, 8 * i);
+            const float bri = __shfl_sync(0xffffffffu, br, 8 * i), bii = __shfl_sync(0xffffffffu, bi, 8 * i);
+            fast_apply_p(ari, aii, bri, bii, y[PA[i]], y[PB[i]]);
+        }
+    }
+    return __popc(flags);
+}
+
+__global__ void __launch_bounds__(512, 1) jacobi_v6(const cf* X, cf* Yout, int* info, long long* clk, int max_sweeps) {
+    extern __shared__ float4 smem_raw[];
+    constexpr int NT = 512, NW = 16;
+    float* Yp = (float*)smem_raw;
+    float* nrm = Yp + N * RS;
+    float* lsc = nrm + N;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    load_planar(Yp, X + (size_t)blockIdx.x * N * N, tid, NT);
+    for (int i = tid; i < N; i += NT) lsc[i] = 0.f;
+    __syncthreads();
+    constexpr int nb = N / 4, mcirc = nb - 1, nrounds = nb - 1, ngroups = nb / 2;
+    int sweeps = 0, status = 1;
+    long long t0 = clock64();
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        // true squared norms: 4^l |y|^2
+        for (int i = warp; i < N; i += NW) {
+            Row r; row_load(r, Yp + i * RS, lane);
+            float2 s2 = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int t = 0; t < 2; ++t) { s2 = __ffma2_rn(r.re[t], r.re[t], s2); s2 = __ffma2_rn(r.im[t], r.im[t], s2); }
+            float sum = s2.x + s2.y;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+            if (lane == 0) nrm[i] = sum * ex2_approx(2.0f * lsc[i]);
+        }
+        __syncthreads();
+        bool big = false;
+        for (int r = 0; r < nrounds; ++r) {
+            const int g = warp;
+            int I, J;
+            if (g == 0) { I = mcirc; J = r; }
+            else { I = (r + g) % mcirc; J = (r - g + mcirc) % mcirc; }
+            float* rowA = Yp + (4 * I) * RS;
+            float* rowB = Yp + (4 * J) * RS;
+            Row v[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                row_load(v[i], rowA + i * RS, lane);
+                row_load(v[4 + i], rowB + i * RS, lane);
+            }
+            int nrot = 0;
+            if (r == 0) {
+                nrot += sub_round_f4<0, 2, 4, 6, 1, 3, 5, 7>(v, nrm, lsc, 4 * I, 4 * J, lane, big);
+                nrot += sub_round_f4<0, 1, 4, 5, 2, 3, 6, 7>(v, nrm, lsc, 4 * I, 4 * J, lane, big);
+                nrot += sub_round_f4<0, 1, 4, 5, 3, 2, 7, 6>(v, nrm, lsc, 4 * I, 4 * J, lane, big);
+            }
+            nrot += sub_round_f4<0, 1, 2, 3, 4, 5, 6, 7>(v, nrm, lsc, 4 * I, 4 * J, lane, big);
+            nrot += sub_round_f4<0, 1, 2, 3, 5, 6, 7, 4>(v, nrm, lsc, 4 * I, 4 * J, lane, big);
+            nrot += sub_round_f4<0, 1, 2, 3, 6, 7, 4, 5>(v, nrm, lsc, 4 * I, 4 * J, lane, big);
+            nrot += sub_round_f4<0, 1, 2, 3, 7, 4, 5, 6>(v, nrm, lsc, 4 * I, 4 * J, lane, big);
+            if (nrot) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    row_store(v[i], rowA + i * RS, lane);
+                    row_store(v[4 + i], rowB + i * RS, lane);
+                }
+            }
+            if (r + 1 < nrounds) neighbour_sync(g, ngroups);
+        }
+        sweeps = sweep + 1;
+        if (!__syncthreads_or(big ? 1 : 0)) { status = 0; break; }
+    }
+    long long t1 = clock64();
+    __syncthreads();
+    // back to true rows
+    for (int i = warp; i < N; i += NW) {
+        const float d = ex2_approx(lsc[i]);
+        for (int c = lane; c < 2 * N; c += 32) Yp[i * RS + c] *= d;
+    }
+    __syncthreads();
+    store_planar(Yp, Yout + (size_t)blockIdx.x * N * N, tid, NT);
+    if (tid == 0) {
+        info[2 * blockIdx.x] = status; info[2 * blockIdx.x + 1] = sweeps;
+        if (blockIdx.x == 0) clk[0] = t1 - t0;
+    }
+}
+
 // ---- 1024 threads, 2-row blocks -----------------------------------------------------------------
 // sub-round of 2 disjoint rotations (A0,B0), (A1,B1): after the 16-step a half-warp owns one pair,
 // after the 8-step a quarter owns its re or im part; one more shuffle fetches the other part.
@@ -762,6 +917,7 @@ int main(int argc, char** argv) {
         {"V0  512 thr, 4-row blocks, interleaved FFMA (production)", jacobi_v0<false>, 512, smem_v0},
         {"V0p the same with per-phase clocks", jacobi_v0<true>, 512, smem_v0},
         {"V2  512 thr, 4-row blocks, planar FFMA2", jacobi_v2, 512, smem_p},
+        {"V6  512 thr, 4-row blocks, planar FFMA2, fast (scaled) rotations", jacobi_v6, 512, smem_p + N * (int)sizeof(float)},
         {"V5  512 thr, 4-row blocks, planar FFMA2, Gram once per round (lite update)", jacobi_v5<false>, 512, smem_p},
         {"V5p the same with per-phase clocks (gram | reduce32 | 4 scalar sub-rounds | apply | load | store | barrier)", jacobi_v5<true>, 512, smem_p},
         {"V3 1024 thr, 2-row blocks, planar FFMA2, __syncthreads per round", jacobi_v3<0>, 1024, smem_p},
