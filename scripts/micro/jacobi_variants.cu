@@ -403,6 +403,79 @@ __global__ void __launch_bounds__(512, 1) jacobi_v2(const cf* X, cf* Yout, int* 
     }
 }
 
+__device__ unsigned g_stagger_ns;
+
+// V7: V2 with half of the warps of every scheduler delayed at the start of each round
+__global__ void __launch_bounds__(512, 1) jacobi_v7(const cf* X, cf* Yout, int* info, long long* clk, int max_sweeps) {
+    extern __shared__ float4 smem_raw[];
+    constexpr int NT = 512, NW = 16;
+    float* Yp = (float*)smem_raw;
+    float* nrm = Yp + N * RS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    load_planar(Yp, X + (size_t)blockIdx.x * N * N, tid, NT);
+    __syncthreads();
+    constexpr int nb = N / 4, mcirc = nb - 1, nrounds = nb - 1, ngroups = nb / 2;
+    int sweeps = 0, status = 1;
+    long long t0 = clock64();
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        refresh_norms(Yp, nrm, warp, lane, NW);
+        __syncthreads();
+        bool big = false;
+        for (int r = 0; r < nrounds; ++r) {
+            // STAGGER: the warps of a scheduler (w, w+4, w+8, w+12) run the rounds in lock-step -- all four in
+            // the FMA-bound apply, then all four in the reduction / parameter latency chains.  Half of them
+            // (w in 4-7, 12-15: two per scheduler) start every round g_stagger_ns later, so that one pair's FMA
+            // phases fall into the other pair's latency phases.
+            if (g_stagger_ns && ((warp >> 2) & 1)) __nanosleep(g_stagger_ns);
+            const int g = warp;
+            int I, J;
+            if (g == 0) { I = mcirc; J = r; }
+            else { I = (r + g) % mcirc; J = (r - g + mcirc) % mcirc; }
+            float* rowA = Yp + (4 * I) * RS;
+            float* rowB = Yp + (4 * J) * RS;
+            Row v[8];
+            float a[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                row_load(v[i], rowA + i * RS, lane);
+                row_load(v[4 + i], rowB + i * RS, lane);
+                a[i] = nrm[4 * I + i];
+                a[4 + i] = nrm[4 * J + i];
+            }
+            int nrot = 0;
+            if (r == 0) {
+                nrot += sub_round_p4<0, 2, 4, 6, 1, 3, 5, 7>(v, a, lane, big);
+                nrot += sub_round_p4<0, 1, 4, 5, 2, 3, 6, 7>(v, a, lane, big);
+                nrot += sub_round_p4<0, 1, 4, 5, 3, 2, 7, 6>(v, a, lane, big);
+            }
+            nrot += sub_round_p4<0, 1, 2, 3, 4, 5, 6, 7>(v, a, lane, big);
+            nrot += sub_round_p4<0, 1, 2, 3, 5, 6, 7, 4>(v, a, lane, big);
+            nrot += sub_round_p4<0, 1, 2, 3, 6, 7, 4, 5>(v, a, lane, big);
+            nrot += sub_round_p4<0, 1, 2, 3, 7, 4, 5, 6>(v, a, lane, big);
+            if (nrot) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    row_store(v[i], rowA + i * RS, lane);
+                    row_store(v[4 + i], rowB + i * RS, lane);
+                }
+                float am = a[0];
+#pragma unroll
+                for (int i = 1; i < 8; ++i) if (lane == i) am = a[i];
+                if (lane < 8) nrm[lane < 4 ? 4 * I + lane : 4 * J + lane - 4] = am;
+            }
+            if (r + 1 < nrounds) neighbour_sync(g, ngroups);
+        }
+        sweeps = sweep + 1;
+        if (!__syncthreads_or(big ? 1 : 0)) { status = 0; break; }
+    }
+    long long t1 = clock64();
+    store_planar(Yp, Yout + (size_t)blockIdx.x * N * N, tid, NT);
+    if (tid == 0) {
+        info[2 * blockIdx.x] = status; info[2 * blockIdx.x + 1] = sweeps;
+        if (blockIdx.x == 0) clk[0] = t1 - t0;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // V5: the Gram entries of a block pair are formed ONCE per round.  One pass over the 8 rows gives the
 // 4 x 4 cross block C[i][j] = <A_i, B_j> (128 FFMA2 per lane), ONE transposed reduction of its 32 real
@@ -924,6 +997,22 @@ int main(int argc, char** argv) {
         {"V4 1024 thr, 2-row blocks, planar FFMA2, grouped named barriers", jacobi_v3<1>, 1024, smem_p},
     };
     cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const unsigned stag_list[] = {0u, 150u, 300u, 500u, 800u, 1200u};
+    for (unsigned stag : stag_list) {
+        cudaMemcpyToSymbol(g_stagger_ns, &stag, sizeof(unsigned));
+        cudaFuncSetAttribute(jacobi_v7, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_p);
+        float ms = 0;
+        for (int rep = 0; rep < 3; ++rep) {
+            cudaEventRecord(e0);
+            jacobi_v7<<<nmat, 512, smem_p>>>(dX, dY, dinfo, dclk, max_sweeps);
+            cudaEventRecord(e1); cudaEventSynchronize(e1);
+            cudaEventElapsedTime(&ms, e0, e1);
+        }
+        std::vector<int> info(nmat * 2); long long clk[256];
+        cudaMemcpy(info.data(), dinfo, info.size() * sizeof(int), cudaMemcpyDeviceToHost);
+        cudaMemcpy(clk, dclk, sizeof(clk), cudaMemcpyDeviceToHost);
+        printf("V7  V2 + stagger %4u ns: %.3f ms per launch, CTA 0: %.0f cycles per sweep (%d sweeps)\n", stag, ms, (double)clk[0] / info[1], info[1]);
+    }
     for (const Variant& v : vs) {
         cudaFuncSetAttribute(v.k, cudaFuncAttributeMaxDynamicSharedMemorySize, v.smem);
         float ms = 0;
