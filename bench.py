@@ -639,8 +639,10 @@ def run_our_arm(args):
         for L in cp.launches:
             if L[0] == "g1":
                 launches_per_step += 1
-            elif L[0] == "g2layer":                   # large-chi layers only (not this workload)
-                launches_per_step += 4 * len(L[1])
+            elif L[0] == "g2layer":                   # the shape groups of one layer, concurrently on library streams
+                for grp in L[1]:
+                    tc = grp["chiL"] >= 32 and grp["chiR"] >= 32 and grp["chiM"] >= 16
+                    launches_per_step += (3 if tc else 1) + 1
             else:
                 _, _, _, chiL, chiM, chiR, _, _ = L
                 tc = chiL >= 32 and chiR >= 32 and chiM >= 16        # api.cu: theta_uses_tc (d = 2)

@@ -312,11 +312,12 @@ class DeviceChain:
                     c = min(per_call, count - c0)
                     layer_groups.append(("g2", start + c0, c, chiL, chiM, chiR, k, int(lc)))
                     ws_need = max(ws_need, lib.mpsb_gate2_workspace_bytes(c, B, d, chiL, chiM, chiR, k))
-            # A layer whose shape classes include the block-Jacobi path (d*chi > 128) goes down as ONE
-            # mpsb_apply_gate2_layer call: its groups run concurrently on library streams, so the
-            # latency-bound one- or two-matrix groups at the chain ends hide behind the main group.
-            # (Layers of small-chi groups only are throughput bound and stay on the caller's stream.)
-            if len(layer_groups) > 1 and any(d * max(g[3], g[5]) > _lib.MAX_SMALL_DIM for g in layer_groups):
+            # A layer with several shape classes goes down as ONE mpsb_apply_gate2_layer call: its groups run
+            # concurrently on library streams.  With block-Jacobi groups (d*chi > 128) the latency-bound one- or
+            # two-matrix groups at the chain ends hide behind the main group (configs[2]: +30 %); with
+            # single-CTA groups only, the ragged-edge groups fill the last partial wave of the main group's
+            # launch (configs[3]: 153.5 k -> 155.2 k applications/s).
+            if len(layer_groups) > 1:
                 launches.append(("g2layer", layer_groups))
             else:
                 launches += layer_groups
