@@ -403,6 +403,70 @@ def time_wavefunction(torch):
                     "8 d^n written (+ the partial products written and re-read)"}
 
 
+def measure_tf32_peak(torch):
+    """Dense TF32 tensor-core throughput measured live (cuBLAS fp32 GEMM with TF32 allowed): the
+    'complex tensor-core peak' of SURVEY.md 8(d) is this / 3 (three TF32 products per fp32 product)."""
+    n = 8192
+    a = torch.randn((n, n), device="cuda", dtype=torch.float32)
+    b = torch.randn((n, n), device="cuda", dtype=torch.float32)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        torch.matmul(a, b)
+        torch.cuda.synchronize()
+        best = 0.0
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 2.0 * n ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        return best
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
+def time_theta_tc(torch, tf32_peak):
+    """theta contraction alone at the large shapes of BASELINE.json (chi = 256: configs[2], 50
+    disjoint bonds of one layer; chi = 1024: configs[4], 8 bonds), tensor-core kernel, CUDA events.
+    frac = achieved / (measured dense TF32 / 3)."""
+    from mpsim_b200 import _lib
+    lib = _lib.load(require_device=True)
+    out = {}
+    for chi, jobs in ((256, 50), (1024, 8)):
+        d = 2
+        A = torch.randn((jobs, chi, d, chi), dtype=torch.complex64, device="cuda")
+        Bm = torch.randn((jobs, chi, d, chi), dtype=torch.complex64, device="cuda")
+        G = torch.from_numpy(haar_gates(jobs, np.random.default_rng(11)).reshape(jobs, 16)).cuda()
+        desc = np.zeros(1, dtype=_lib.GATE2_DESC)
+        desc[0] = (A.data_ptr(), Bm.data_ptr(), 0, 0, G.data_ptr(), 0, chi * d * chi, chi * d * chi, 0, 0, 16, 0)
+        ddesc = _lib.to_device_bytes(desc, "cuda")
+        theta = torch.empty((jobs, d * chi, d * chi), dtype=torch.complex64, device="cuda")
+        ws = torch.empty(lib.mpsb_theta_workspace_bytes(1, jobs, d, chi, chi, chi) + 256, dtype=torch.uint8, device="cuda")
+
+        def run():
+            _lib.check(lib.mpsb_theta(ddesc.data_ptr(), 1, jobs, d, chi, chi, chi, theta.data_ptr(), ws.data_ptr(),
+                                      ws.numel(), _lib.stream_ptr()))
+        for _ in range(3):
+            run()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(5):
+            run()
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 5
+        fl = flops_theta(d, chi, chi, chi) * jobs
+        tf = fl / (ms * 1e-3) / 1e12
+        out[f"chi{chi}"] = {"jobs": jobs, "ms_per_launch": ms, "tflops_complex_equivalent": tf,
+                            "complex_tensor_core_peak_tflops": tf32_peak / 3.0, "frac_of_complex_peak": tf / (tf32_peak / 3.0),
+                            "note": "includes the operand split / transpose kernels; operands %.0f MB > L2 at chi=1024"
+                                    % (2 * jobs * chi * d * chi * 8 / 1e6)}
+        del A, Bm, theta, ws
+    return out
+
+
 def cpu_dominant_shape(chi, reps):
     """The reference's CPU arithmetic for ONE adjacent application of shape (chi, chi, chi, k = chi):
     the complex128 numpy/LAPACK oracle (mpsim/core.py:1060-1152 restated) on random sites, all host
