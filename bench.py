@@ -380,15 +380,17 @@ def time_wavefunction(torch):
     mps = mp.MPS(n)
     mps._execute([(o.tensor, o.indices, {"maxsvals": chi, "keep_left_canonical": o.keep_left_canonical})
                   for o in circuits.brickwork(n, depth, seed=9)])
-    mps.wavefunction_device()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    reps = 3
-    e0.record()
-    for _ in range(reps):
+    for _ in range(3):
         wf = mps.wavefunction_device()
-    e1.record(); torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / reps
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(5):                                       # every repetition timed on its own
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        wf = mps.wavefunction_device()
+        e1.record(); torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = float(np.median(times))
     out_bytes = 8.0 * 2 ** n
     # partial products of the two-sided contraction (api.cu: wf_plan picks the split that minimises them):
     # each is written once and read once
@@ -397,7 +399,7 @@ def time_wavefunction(torch):
     Rs = [2.0 ** (n - i) * bonds[i] for i in range(n)]
     inter = min(sum(Ls[1:sp]) + sum(Rs[sp:n - 1]) for sp in range(1, n))
     del wf
-    return {"nqubits": n, "chi": chi, "ms": ms, "gbs_output_written": out_bytes / (ms * 1e-3) / 1e9,
+    return {"nqubits": n, "chi": chi, "ms": ms, "ms_all_repetitions": times, "gbs_output_written": out_bytes / (ms * 1e-3) / 1e9,
             "gbs_with_partial_products": (out_bytes + 16.0 * inter) / (ms * 1e-3) / 1e9,
             "note": "left and right chains of strided complex GEMMs joined by one product (tcgen05 kernel); bytes = "
                     "8 d^n written (+ the partial products written and re-read)"}
