@@ -477,6 +477,143 @@ __global__ void __launch_bounds__(512, 1) jacobi_v7(const cf* X, cf* Yout, int* 
 }
 
 // ------------------------------------------------------------------------------------------------
+// V8: V2 with the FMA-heavy apply phases of the two warp pairs of a scheduler forced to ALTERNATE.  Warps w and
+// w ^ 4 share a scheduler; each passes a token (two mbarriers per pair, one arrival per apply) so that one of
+// them applies its rotations while the other is in its reduction / parameter latency chain, instead of all
+// four warps of the scheduler contending for the FMA pipe at once and then idling at once.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32_(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init_(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32_(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive_(unsigned long long* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32_(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_(unsigned long long* bar, unsigned parity) {
+    unsigned ok = 0;
+    while (!ok) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32_(bar)), "r"(parity) : "memory");
+    }
+}
+
+template <int A0, int A1, int A2, int A3, int B0, int B1, int B2, int B3>
+__device__ __forceinline__ int sub_round_t4(Row (&y)[8], float (&a)[8], int lane, bool& big,
+                                            unsigned long long* mine, unsigned long long* partner, bool lower, unsigned& k) {
+    constexpr int PA[4] = {A0, A1, A2, A3}, PB[4] = {B0, B1, B2, B3};
+    float gr[4], gi[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gram_part(y[PA[i]], y[PB[i]], gr[i], gi[i]);
+    const float mgr = reduce4(gr, lane), mgi = reduce4(gi, lane);
+    const int sel = lane >> 3;
+    float ap = a[PA[0]], aq = a[PB[0]];
+#pragma unroll
+    for (int i = 1; i < 4; ++i) if (sel == i) { ap = a[PA[i]]; aq = a[PB[i]]; }
+    const float g2 = fmaf(mgr, mgr, mgi * mgi), apq = ap * aq;
+    float c = 1.f, sr = 0.f, si = 0.f, tg = 0.f;
+    const bool dorot = (g2 > TOL2 * apq) && (g2 > 1e-30f);
+    big = big || (dorot && g2 > BIG2 * apq);
+    if (dorot) rot_params(ap, aq, mgr, mgi, g2, c, sr, si, tg);
+    const unsigned bal = __ballot_sync(0xffffffffu, dorot);
+    const unsigned flags = (bal & 1u) | ((bal >> 7) & 2u) | ((bal >> 14) & 4u) | ((bal >> 21) & 8u);
+    // token: the lower warp's k-th apply waits for the partner's (k-1)-th, the partner's k-th for the lower's k-th
+    if (lower) { if (k > 0) mbar_wait_(partner, (k - 1) & 1u); }
+    else mbar_wait_(partner, k & 1u);
+    int n = 0;
+    if (flags) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (flags & (1u << i)) {
+                const float ci = __shfl_sync(0xffffffffu, c, 8 * i);
+                const float sri = __shfl_sync(0xffffffffu, sr, 8 * i);
+                const float sii = __shfl_sync(0xffffffffu, si, 8 * i);
+                const float tgi = __shfl_sync(0xffffffffu, tg, 8 * i);
+                rot_apply_p(ci, sri, sii, y[PA[i]], y[PB[i]]);
+                a[PA[i]] = fmaxf(a[PA[i]] + tgi, 0.f);
+                a[PB[i]] = fmaxf(a[PB[i]] - tgi, 0.f);
+            }
+        }
+        n = __popc(flags);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive_(mine);
+    ++k;
+    return n;
+}
+
+__global__ void __launch_bounds__(512, 1) jacobi_v8(const cf* X, cf* Yout, int* info, long long* clk, int max_sweeps) {
+    extern __shared__ float4 smem_raw[];
+    __shared__ __align__(8) unsigned long long tok[16];
+    constexpr int NT = 512, NW = 16;
+    float* Yp = (float*)smem_raw;
+    float* nrm = Yp + N * RS;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 16) mbar_init_(&tok[tid], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    load_planar(Yp, X + (size_t)blockIdx.x * N * N, tid, NT);
+    __syncthreads();
+    unsigned long long* mine = &tok[warp];
+    unsigned long long* partner = &tok[warp ^ 4];
+    const bool lower = (warp & 4) == 0;
+    unsigned k = 0;
+    constexpr int nb = N / 4, mcirc = nb - 1, nrounds = nb - 1, ngroups = nb / 2;
+    int sweeps = 0, status = 1;
+    long long t0 = clock64();
+    for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+        refresh_norms(Yp, nrm, warp, lane, NW);
+        __syncthreads();
+        bool big = false;
+        for (int r = 0; r < nrounds; ++r) {
+            const int g = warp;
+            int I, J;
+            if (g == 0) { I = mcirc; J = r; }
+            else { I = (r + g) % mcirc; J = (r - g + mcirc) % mcirc; }
+            float* rowA = Yp + (4 * I) * RS;
+            float* rowB = Yp + (4 * J) * RS;
+            Row v[8];
+            float a[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                row_load(v[i], rowA + i * RS, lane);
+                row_load(v[4 + i], rowB + i * RS, lane);
+                a[i] = nrm[4 * I + i];
+                a[4 + i] = nrm[4 * J + i];
+            }
+            int nrot = 0;
+            if (r == 0) {
+                nrot += sub_round_t4<0, 2, 4, 6, 1, 3, 5, 7>(v, a, lane, big, mine, partner, lower, k);
+                nrot += sub_round_t4<0, 1, 4, 5, 2, 3, 6, 7>(v, a, lane, big, mine, partner, lower, k);
+                nrot += sub_round_t4<0, 1, 4, 5, 3, 2, 7, 6>(v, a, lane, big, mine, partner, lower, k);
+            }
+            nrot += sub_round_t4<0, 1, 2, 3, 4, 5, 6, 7>(v, a, lane, big, mine, partner, lower, k);
+            nrot += sub_round_t4<0, 1, 2, 3, 5, 6, 7, 4>(v, a, lane, big, mine, partner, lower, k);
+            nrot += sub_round_t4<0, 1, 2, 3, 6, 7, 4, 5>(v, a, lane, big, mine, partner, lower, k);
+            nrot += sub_round_t4<0, 1, 2, 3, 7, 4, 5, 6>(v, a, lane, big, mine, partner, lower, k);
+            if (nrot) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    row_store(v[i], rowA + i * RS, lane);
+                    row_store(v[4 + i], rowB + i * RS, lane);
+                }
+                float am = a[0];
+#pragma unroll
+                for (int i = 1; i < 8; ++i) if (lane == i) am = a[i];
+                if (lane < 8) nrm[lane < 4 ? 4 * I + lane : 4 * J + lane - 4] = am;
+            }
+            if (r + 1 < nrounds) neighbour_sync(g, ngroups);
+        }
+        sweeps = sweep + 1;
+        if (!__syncthreads_or(big ? 1 : 0)) { status = 0; break; }
+    }
+    long long t1 = clock64();
+    store_planar(Yp, Yout + (size_t)blockIdx.x * N * N, tid, NT);
+    if (tid == 0) {
+        info[2 * blockIdx.x] = status; info[2 * blockIdx.x + 1] = sweeps;
+        if (blockIdx.x == 0) clk[0] = t1 - t0;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // V5: the Gram entries of a block pair are formed ONCE per round.  One pass over the 8 rows gives the
 // 4 x 4 cross block C[i][j] = <A_i, B_j> (128 FFMA2 per lane), ONE transposed reduction of its 32 real
 // numbers leaves entry (i, j) on lane pair 8i + 2j (+1: im), and the four sub-rounds then run on those
@@ -990,6 +1127,7 @@ int main(int argc, char** argv) {
         {"V0  512 thr, 4-row blocks, interleaved FFMA (production)", jacobi_v0<false>, 512, smem_v0},
         {"V0p the same with per-phase clocks", jacobi_v0<true>, 512, smem_v0},
         {"V2  512 thr, 4-row blocks, planar FFMA2", jacobi_v2, 512, smem_p},
+        {"V8  V2 + apply phases of scheduler-mates alternate (mbarrier token)", jacobi_v8, 512, smem_p},
         {"V6  512 thr, 4-row blocks, planar FFMA2, fast (scaled) rotations", jacobi_v6, 512, smem_p + N * (int)sizeof(float)},
         {"V5  512 thr, 4-row blocks, planar FFMA2, Gram once per round (lite update)", jacobi_v5<false>, 512, smem_p},
         {"V5p the same with per-phase clocks (gram | reduce32 | 4 scalar sub-rounds | apply | load | store | barrier)", jacobi_v5<true>, 512, smem_p},
