@@ -92,26 +92,35 @@ __global__ void bj_init_kernel(LargeParams p) {
         for (int g = threadIdx.x; g < p.npairs; g += blockDim.x) p.gcount[(size_t)job * p.npairs + g] = 0;
 }
 
+__device__ __forceinline__ float rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ void evd_rot_params(float a, float b, float gr, float gi, float g2,
                                                float& c, float& sr, float& si) {
-    // On the critical path of every rotation set (16-31 dependent sets per launch): four MUFU
-    // approximations instead of an IEEE division and square root.  The angle only has to be close
-    // to the annihilating one; unitarity comes from c being DERIVED from s (and from the
-    // Newton-Schulz step on Q).
-    float rg = rsqrtf(g2);
-    float zeta = (a - b) * (0.5f * rg);
-    float az = fminf(fabsf(zeta), 1e18f);                    // keeps az^2 finite
-    float z2 = fmaf(az, az, 1.0f);
-    float t = copysignf(__fdividef(1.0f, az + z2 * rsqrtf(z2)), zeta);
-    float ct = (t * rsqrtf(fmaf(t, t, 1.0f))) * rg;
-    sr = ct * gr;
-    si = ct * gi;
-    float h = fmaf(sr, sr, si * si);
-    if (h < 0.0625f) {
-        float poly = fmaf(h, fmaf(h, fmaf(h, fmaf(h, 0.02734375f, 0.0390625f), 0.0625f), 0.125f), 0.5f);
-        c = fmaf(-h, poly, 1.0f);
+    // On the critical path of every rotation set (16-31 dependent sets per launch).  The same two-MUFU form
+    // as svd_small.cu: d = a - b, h = sqrt(d^2 + 4|g|^2), w = h + |d|, |s|^2 = 2|g|^2 / (h w); the Gram
+    // matrix is scaled to max|G| in [1, 2) and a rotation needs |g|^2 > 1e-30, so the arguments of the
+    // approximations stay in range.  The angle only has to be close to the annihilating one; unitarity comes
+    // from c being DERIVED from s (and from the Newton-Schulz step on Q).
+    const float d = a - b;
+    const float u = fmaf(d, d, 4.0f * g2);
+    const float h = u * rsqrt_approx(u);
+    const float w = h + fabsf(d);
+    const float k = copysignf(1.41421356f, d) * rsqrt_approx(h * w);
+    sr = gr * k;
+    si = gi * k;
+    const float hh = fmaf(sr, sr, si * si);
+    if (hh < 0.0625f) {
+        const float poly = fmaf(hh, fmaf(hh, fmaf(hh, fmaf(hh, 0.02734375f, 0.0390625f), 0.0625f), 0.125f), 0.5f);
+        c = fmaf(-hh, poly, 1.0f);
     } else {
-        c = sqrtf(fmaf(-sr, sr, fmaf(-si, si, 1.0f)));
+        const float y = fmaf(-sr, sr, fmaf(-si, si, 1.0f));
+        const float r0 = rsqrt_approx(y);
+        const float c0 = y * r0;
+        c = fmaf(0.5f * r0, fmaf(-c0, c0, y), c0);
     }
 }
 
