@@ -406,6 +406,33 @@ def test_simulator_ghz_qft_and_sweep():                     # simulator_test.py:
         MPSimulator().simulate("not a circuit")
 
 
+def test_simulator_ghz_qft_maxsvals128_block_jacobi():
+    """The regime of BASELINE configs[1] (GHZ + QFT through MPSimulator, maxsvals = 128) at a size whose
+    wavefunction is computable: 14 qubits, bonds inflate to 128 (zeros are kept, core_test.py:932-944), the
+    swap networks run ~700 adjacent applications, those with d chi > 128 on the block-Jacobi path with
+    rank-deficient thetas.  Nothing physical is truncated (the true ranks are tiny), so the state must equal
+    the dense simulation."""
+    from mpsim_b200.mpsim_cirq import MPSimulator
+    from tests._fake_cirq import Circuit, H, CNOT, CZPow
+    n = 14
+    ops = [H(0)] + [CNOT(0, i) for i in range(1, n)]
+    for i in range(n - 1, -1, -1):
+        ops.append(H(i))
+        for j in range(i - 1, -1, -1):
+            ops.append(CZPow(2.0 ** (j - i), j, i))
+    circ = Circuit(ops)
+    dense = DenseState(n)
+    for op in circ.all_operations():
+        dense.apply(np.asarray(op._unitary_()).reshape((2,) * (2 * len(op.qubits))), op.qubits)
+    mps = MPSimulator({"maxsvals": 128}).simulate(circ)
+    assert max(mps.bond_dimensions()) == 128
+    assert (mps.last_status()[:, 0] == 0).all()
+    wf, ref = mps.wavefunction(), dense.wavefunction()
+    np.testing.assert_allclose(wf, ref, atol=AMP_TOL)
+    assert fidelity(wf, ref) >= 1 - FID_TOL
+    assert abs(mps.norm() - 1.0) < 1e-4
+
+
 @pytest.mark.parametrize("nqubits", [2, 4, 8])
 def test_simulator_random_circuits(nqubits):                # simulator_test.py:274-305
     """50 random circuits of 25 moments over the reference's gate domain (X, Y, Z, H, S, T, CNOT, CZ, SWAP,
