@@ -19,8 +19,15 @@
 // The tensor core truncates (round-toward-zero) once per accumulating MMA, which shrinks a long
 // accumulation systematically: measured rms error 2.8e-7 / 9.5e-7 / 4.5e-6 / 8.3e-6 of max|C| at
 // K = 64 / 256 / 1024 / 2048 when a whole K loop runs in one accumulator (scripts/tc_accuracy.py).
-// The K loop is therefore cut into chunks of KCH k-blocks (64 complex k): each chunk accumulates
-// in TMEM from zero and the epilogue warps add the chunks in fp32 registers with round-to-nearest.
+// The K loop is therefore cut into chunks of KCH k-blocks: each chunk accumulates in TMEM from zero
+// and the epilogue warps add the chunks in fp32 registers with round-to-nearest.  Round 1 used chunks
+// of 4 k-blocks (64 complex k, 48 MMAs): rms error fine, but the truncation is a systematic SHRINK --
+// a 14-qubit GHZ + QFT circuit (about 700 applications, nothing truncated) lost 2.6e-4 of its norm,
+// 3.7e-7 per application, against +3e-5 with the FFMA theta kernel.  With one k-block per chunk
+// (16 complex k, 12 MMAs; the two TMEM accumulators still alternate, so draining chunk c overlaps the
+// MMAs of chunk c+1) the loss is 3e-5, the noise level of the FFMA kernel; the price is one TMEM drain
+// per k-block: theta at chi = 1024 1.42 -> 1.54 ms (0.76 -> 0.71 of the complex tensor-core peak), chi =
+// 256 0.271 -> 0.300 ms (scripts/norm_bias_ghz_qft.py, bench.py; MPSB_TC_KCH=n overrides for A/B).
 //
 // Kernel structure (persistent, one CTA per SM, 640 threads):
 //   warp 0   : TMA producer -- per k-block four boxes (A_hi, A_lo: 128 x 32 fp32; B_hi, B_lo:
@@ -49,7 +56,7 @@ constexpr int B_TILE_BYTES = BNR * BK * 4;       // 32 KB
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;     // 96 KB
 constexpr int TC_THREADS = 640;        // producer, MMA, 2 idle warps (registers are allocated per 4 warps) + 16 epilogue warps
 constexpr int CPT = 64;                // accumulator columns per epilogue thread
-constexpr int KCH = 4;           // k-blocks per accumulation chunk
+constexpr int KCH = 1;           // k-blocks per accumulation chunk (see the header: truncation bias)
 constexpr int RB = 64;           // r values per tile (two column halves of 32, each with q = 0 | q = 1)
 // kind::tf32, fp32 accumulate, A and B K-major, M = 128, N = 256
 constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BNR >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
@@ -57,6 +64,7 @@ constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)
 struct TcParams {
     int njobs, nbatch;           // jobs = ndesc * nbatch
     int mtiles, ntiles, nkb;     // tiles per job, k-blocks
+    int kch;                     // k-blocks per accumulation chunk
     int M, chiR;                 // valid rows (2 chiL) and r values (mode 1) / valid complex columns (mode 0)
     int mode;                    // 1: theta epilogue (gate, optional transpose); 0: plain complex C store
     int transpose_out;
@@ -115,11 +123,11 @@ tc_cgemm_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_consta
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int tile = blockIdx.x; tile < ntile_total; tile += gridDim.x) {
-                for (int kb0 = 0; kb0 < P.nkb; kb0 += KCH) {
+                for (int kb0 = 0; kb0 < P.nkb; kb0 += P.kch) {
                     mbar_wait(&acc_empty[acc], acc_phase ^ 1);
                     tc_fence_after();
                     const uint32_t tmem_d = tmem_base + (uint32_t)acc * BNR;
-                    const int kb1 = min(kb0 + KCH, P.nkb);
+                    const int kb1 = min(kb0 + P.kch, P.nkb);
                     for (int kb = kb0; kb < kb1; ++kb) {
                         mbar_wait(&full_bar[stage], phase);
                         tc_fence_after();
@@ -154,7 +162,7 @@ tc_cgemm_kernel(const __grid_constant__ CUtensorMap map_ahi, const __grid_consta
             float sum[CPT];
 #pragma unroll
             for (int i = 0; i < CPT; ++i) sum[i] = 0.f;
-            for (int kb0 = 0; kb0 < P.nkb; kb0 += KCH) {
+            for (int kb0 = 0; kb0 < P.nkb; kb0 += P.kch) {
                 mbar_wait(&acc_full[acc], acc_phase);
                 tc_fence_after();
                 const uint32_t trow = tmem_base + (uint32_t)acc * BNR + (uint32_t)cq * CPT + ((uint32_t)(wq * 32) << 16);
@@ -403,6 +411,8 @@ int run_tc(int mode, int njobs, int nbatch, const mpsb_gate2_desc* descs, const 
     TcParams P;
     P.njobs = njobs; P.nbatch = nbatch > 0 ? nbatch : 1;
     P.mtiles = lo.mtiles; P.ntiles = lo.ntiles; P.nkb = lo.nkb;
+    P.kch = KCH;
+    if (const char* e = mpsb_env("MPSB_TC_KCH")) { const int v = atoi(e); if (v >= 1 && v <= 64) P.kch = v; }
     P.M = Mc; P.chiR = Nc_or_chiR; P.mode = mode; P.transpose_out = transpose_out;
     P.descs = descs; P.out = out; P.out_job_stride = out_job_stride; P.out_ld = out_ld;
     int dev = 0, sms = 148;

@@ -45,9 +45,9 @@ SV_TOL = 1e-5          # relative to sigma_max of the application, and per kept 
 # trace was 1.3e-3 before and 4.3e-3 after the sweep engine went to packed FFMA2 -- which is what amplification
 # of rounding differences looks like):
 #                         sigma trace   norm      infidelity   amplitude/rms
-#   config3_member0/511   2.2e-4        4.0e-4    6.7e-5       2.6e-2          (single-CTA path only)
-#   snake_4x4_chi96       4.3e-3        1.0e-4    1.7e-3       1.0e-1
-#   config2_full          1.8e-3        8.9e-4    1.8e-2       3.3e-1
+#   config3_member0/511   4.2e-4        2.1e-4    7.5e-5       3.0e-2          (single-CTA path only)
+#   snake_4x4_chi96       4.0e-3        0.7e-4    1.6e-3       0.9e-1
+#   config2_full          1.9e-3        3.6e-4    1.9e-2       4.4e-1
 # For scale, the complex128 oracle run in complex64 (numpy / LAPACK cgesdd) deviates from its own
 # complex128 run by 2e-5 ... 2e-4 in the singular-value trace, 3e-6 ... 7e-6 in the norm, 2e-7 ... 4e-6 in
 # sampled infidelity and 2e-3 ... 5e-3 of the rms amplitude: the GPU path is 10 (single-CTA path) to 60 times
@@ -74,7 +74,7 @@ def _check_sigma(name, svals_per_app, base, tol=SV_TOL):
     on the single-CTA path (d chi <= 128: one-sided Jacobi on R is relatively accurate; measured 2.2e-6),
     <= 2e-5 for kept values >= 1e-2 sigma_max on the block-Jacobi path (d chi > 128: its rotations come
     from fp32 Gram matrices and accumulated 32 x 32 unitaries whose entries carry ~1e-7 ABSOLUTE error;
-    measured 1.1e-5 on a value of 0.67 sigma_max of the swap-network fixture, 4.2e-6 on configs[2])."""
+    measured 7.7e-6 on the swap-network fixture, 1.4e-6 on configs[2])."""
     worst_max = worst_small = worst_large = 0.0
     for t, (got, k, ref, chi) in enumerate(zip(svals_per_app, base.k, base.svals, base.app_chi)):
         large = 2 * max(chi[0], chi[2]) > 128
