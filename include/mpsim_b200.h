@@ -110,6 +110,16 @@ int mpsb_inner_products(const mpsb_site_ref* a_host, const mpsb_site_ref* b_host
 int mpsb_scale_sites(const mpsb_site_ref* sites_dev, int nsites, int nbatch, int d,
                      const float* factors_dev, int max_site_elems, void* stream);
 
+/* Gauge rebalance of every batch member's chain: when the binary exponents of the sites' largest
+ * entries are more than spread_log2 apart, multiply each site by a power of two so that they
+ * agree; the shifts of a chain sum to zero, so the state is unchanged bit for bit.  No reference
+ * counterpart: the reference stores complex128, whose exponent range absorbs the drift of its
+ * alternating left/right-canonical sweeps (mpsim/core.py:1348-1360); complex64 storage needs this
+ * after a few hundred layers.  shifts_dev: int32 [nsites][nbatch] scratch, holds the applied
+ * shifts on return. */
+int mpsb_rebalance_sites(const mpsb_site_ref* sites_dev, int nsites, int nbatch, int d, int spread_log2,
+                         int* shifts_dev, int max_site_elems, void* stream);
+
 /* Dense wavefunction of one batch member, big-endian (core.py:483-500): out complex64[d^n].
  * workspace >= mpsb_wavefunction_workspace_bytes(). */
 size_t mpsb_wavefunction_workspace_bytes(const mpsb_site_ref* sites_host, int nsites, int d);

@@ -50,6 +50,7 @@ SYMBOLS = {
     "mpsb_inner_workspace_bytes": (c_size_t, [c_int] * 4),
     "mpsb_inner_products": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mpsb_scale_sites": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
+    "mpsb_rebalance_sites": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]),
     "mpsb_wavefunction_workspace_bytes": (c_size_t, [c_void_p, c_int, c_int]),
     "mpsb_wavefunction": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mpsb_amplitudes": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p]),

@@ -13,6 +13,8 @@ int launch_scale(const mpsb_site_ref* sites, int nsites, int nbatch, int d, cons
                  int max_site_elems, cudaStream_t st);
 int launch_amplitudes(const mpsb_site_ref* sites, int nsites, int nbatch, int d, int max_chi,
                       const uint8_t* bits, int nbits, cf* out, cudaStream_t st);
+int launch_rebalance(const mpsb_site_ref* sites, int nsites, int nbatch, int d, int spread, int* shifts,
+                     int max_site_elems, cudaStream_t st);
 
 static thread_local char g_err[512] = "";
 
@@ -360,6 +362,13 @@ int mpsb_scale_sites(const mpsb_site_ref* sites_dev, int nsites, int nbatch, int
                      const float* factors_dev, int max_site_elems, void* stream) {
     MPSB_ARG(sites_dev && factors_dev, "scale_sites: NULL argument");
     return launch_scale(sites_dev, nsites, nbatch, d, factors_dev, max_site_elems, (cudaStream_t)stream);
+}
+
+int mpsb_rebalance_sites(const mpsb_site_ref* sites_dev, int nsites, int nbatch, int d, int spread_log2,
+                         int* shifts_dev, int max_site_elems, void* stream) {
+    MPSB_ARG(sites_dev && shifts_dev, "rebalance_sites: NULL argument");
+    MPSB_ARG(spread_log2 >= 0, "rebalance_sites: negative spread");
+    return launch_rebalance(sites_dev, nsites, nbatch, d, spread_log2, shifts_dev, max_site_elems, (cudaStream_t)stream);
 }
 
 // Dense wavefunction of one chain: contracted from BOTH ends and joined by one product,

@@ -1,4 +1,5 @@
 // HBM-bound site kernels: one-qudit gate, per-chain scaling, amplitude chains.
+#include <climits>
 #include "common.cuh"
 
 namespace {
@@ -122,6 +123,74 @@ amplitude_kernel(const mpsb_site_ref* __restrict__ sites, int nsites, int nbatch
     if (threadIdx.x == 0) out[(size_t)bi * nbits + bit_id] = cur[0];
 }
 
+// ---- gauge rebalance -------------------------------------------------------------------------
+// The reference's sweep pattern (even layers left-canonical, odd layers right-canonical,
+// mpsim/core.py:1348-1360) leaves the SCALE of the individual site tensors free: only the product
+// is fixed, and in a long circuit it migrates geometrically (in a 12-qubit brickwork one site
+// reaches 1e-37 and two others 1e18 after 240 layers -- the complex128 reference shows the same
+// numbers and has the exponent range for it, complex64 storage does not).  These three kernels
+// move powers of two between the sites of one chain so that every site's largest entry has about
+// the same exponent.  The shifts of a chain sum to zero and a power-of-two scaling is exact, so the
+// state (norm, amplitudes, every contraction) is unchanged bit for bit.
+
+// pass 1: bit pattern of max |re|, |im| over the finite entries of each (site, member)
+__global__ void __launch_bounds__(256)
+site_maxabs_kernel(const mpsb_site_ref* __restrict__ sites, int nbatch, int d, unsigned* __restrict__ maxbits) {
+    const int job = blockIdx.x;
+    const int si = job / nbatch, bi = job % nbatch;
+    const mpsb_site_ref s = sites[si];
+    const float* A = (const float*)((const cf*)s.site + (int64_t)bi * s.bs);
+    const int64_t n = 2 * (int64_t)s.chiL * d * s.chiR;
+    unsigned mx = 0;
+    for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.y * blockDim.x) {
+        unsigned b = __float_as_uint(A[e]) & 0x7fffffffu;
+        if (b < 0x7f800000u && b > mx) mx = b;
+    }
+    for (int o = 16; o; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0 && mx) atomicMax(&maxbits[job], mx);
+}
+
+// pass 2: one thread per member turns the maxima into shifts (in place, as int).  Nothing moves
+// while the exponents of a chain are within `spread` of each other.
+__global__ void rebalance_shift_kernel(unsigned* __restrict__ maxbits, int nsites, int nbatch, int spread) {
+    const int bi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (bi >= nbatch) return;
+    int lo = INT_MAX, hi = INT_MIN, cnt = 0, last = -1;
+    long long sum = 0;
+    for (int s = 0; s < nsites; ++s) {
+        unsigned b = maxbits[(size_t)s * nbatch + bi];
+        if (!b) continue;
+        int e = ilogbf(__uint_as_float(b));
+        lo = min(lo, e); hi = max(hi, e); sum += e; ++cnt; last = s;
+    }
+    const bool act = cnt > 1 && hi - lo > spread;
+    const int mean = act ? (int)floorf((float)sum / (float)cnt) : 0;
+    int given = 0;
+    for (int s = 0; s < nsites; ++s) {
+        unsigned b = maxbits[(size_t)s * nbatch + bi];
+        int sh = 0;
+        if (act && b) {
+            if (s == last) sh = -given;
+            else { sh = mean - ilogbf(__uint_as_float(b)); given += sh; }
+        }
+        ((int*)maxbits)[(size_t)s * nbatch + bi] = sh;
+    }
+}
+
+// pass 3: site <- 2^shift * site (CTAs of an unshifted site leave at once)
+__global__ void __launch_bounds__(256)
+rebalance_apply_kernel(const mpsb_site_ref* __restrict__ sites, int nbatch, int d, const int* __restrict__ shifts) {
+    const int job = blockIdx.x;
+    const int sh = shifts[job];
+    if (sh == 0) return;
+    const int si = job / nbatch, bi = job % nbatch;
+    const mpsb_site_ref s = sites[si];
+    float* A = (float*)((cf*)s.site + (int64_t)bi * s.bs);
+    const int64_t n = 2 * (int64_t)s.chiL * d * s.chiR;
+    for (int64_t e = (int64_t)blockIdx.y * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.y * blockDim.x)
+        A[e] = scalbnf(A[e], sh);
+}
+
 }  // namespace
 
 int launch_gate1(const mpsb_gate1_desc* descs, int ndesc, int nbatch, int d, int max_site_elems, cudaStream_t st) {
@@ -154,6 +223,24 @@ int launch_scale(const mpsb_site_ref* sites, int nsites, int nbatch, int d, cons
     if (bx > 1184) bx = 1184;
     scale_kernel<<<dim3(bx, njobs), 256, 0, st>>>(sites, nbatch, d, factors);
     MPSB_LAUNCH_CHECK("scale_kernel");
+    return 0;
+}
+
+int launch_rebalance(const mpsb_site_ref* sites, int nsites, int nbatch, int d, int spread, int* shifts,
+                     int max_site_elems, cudaStream_t st) {
+    const long long njobs = (long long)nsites * nbatch;
+    if (njobs <= 0) return 0;
+    MPSB_ARG(njobs < (1ll << 31), "rebalance: too many (site, member) pairs (%lld)", njobs);
+    int by = (2 * max_site_elems + 2047) / 2048;          // 8 values per thread
+    if (by < 1) by = 1;
+    if (by > 64) by = 64;
+    MPSB_CUDA(cudaMemsetAsync(shifts, 0, (size_t)njobs * sizeof(int), st));
+    site_maxabs_kernel<<<dim3((unsigned)njobs, by), 256, 0, st>>>(sites, nbatch, d, (unsigned*)shifts);
+    MPSB_LAUNCH_CHECK("site_maxabs_kernel");
+    rebalance_shift_kernel<<<(nbatch + 127) / 128, 128, 0, st>>>((unsigned*)shifts, nsites, nbatch, spread);
+    MPSB_LAUNCH_CHECK("rebalance_shift_kernel");
+    rebalance_apply_kernel<<<dim3((unsigned)njobs, by), 256, 0, st>>>(sites, nbatch, d, shifts);
+    MPSB_LAUNCH_CHECK("rebalance_apply_kernel");
     return 0;
 }
 

@@ -23,6 +23,11 @@ from mpsim_b200 import _lib
 from mpsim_b200.planner import Plan
 
 MAX_JOBS_PER_CALL = 65535
+#: run() checks the spread of the site exponents after this many brickwork layers' worth of
+#: two-site applications (n // 2 each), and rebalances a chain whose sites are further apart than
+#: 2**REBALANCE_SPREAD_LOG2 (see DeviceChain.rebalance)
+REBALANCE_EVERY_LAYERS = 32
+REBALANCE_SPREAD_LOG2 = 32
 
 
 def _torch():
@@ -93,6 +98,7 @@ class CompiledPlan:
         self.plan: Optional[Plan] = None
         self.bonds_out: List[int] = []
         self.n_launch_calls = 0
+        self.n_rebalance_calls = 0
 
 
 class DeviceChain:
@@ -111,6 +117,8 @@ class DeviceChain:
             self.caps[0] = self.caps[-1] = 1
         self._layout_gen = 0
         self._status_flags = []          # device scalars: max SVD status of every run() since the last check
+        self._apps_since_rebalance = 0
+        self._rebalance_bufs = None
         self._ring: List[_Staging] = []
         self._ring_next = 0
         with torch.cuda.device(self.device):
@@ -151,6 +159,7 @@ class DeviceChain:
     def reset(self) -> None:
         """|0...0> on every batch member (``mpsim/core.py:190-218``)."""
         self.bonds = [1] * (self.n + 1)
+        self._apps_since_rebalance = 0
         self.slab.zero_()
         idx = _torch().tensor(self.offs, device=self.device, dtype=_torch().long)
         self.slab[:, idx] = 1.0
@@ -191,6 +200,7 @@ class DeviceChain:
         new._workspace = None
         new._layout_gen = 0
         new._status_flags = list(self._status_flags)
+        new._apps_since_rebalance, new._rebalance_bufs = self._apps_since_rebalance, None
         new._ring, new._ring_next = [], 0
         return new
 
@@ -205,6 +215,7 @@ class DeviceChain:
         new._workspace = None
         new._layout_gen = 0
         new._status_flags = []
+        new._apps_since_rebalance, new._rebalance_bufs = self._apps_since_rebalance, None
         new._ring, new._ring_next = [], 0
         return new
 
@@ -372,6 +383,7 @@ class DeviceChain:
         ws = self.workspace(cp.workspace_bytes)
         st = _lib.stream_ptr()
         d, B = self.d, self.B
+        cp.n_rebalance_calls = 0
         p1, p2, pi = cp.desc1.data_ptr(), cp.desc2.data_ptr(), cp.info.data_ptr()
         for L in cp.launches:
             if L[0] == "g1":
@@ -382,12 +394,17 @@ class DeviceChain:
                 tab = L[1]
                 _lib.check(lib.mpsb_apply_gate2_layer(tab.ctypes.data, len(tab), B, d, ws.data_ptr(), ws.numel(), st),
                            "mpsb_apply_gate2_layer")
+                self._apps_since_rebalance += int(tab["ndesc"].sum())
             else:
                 _, off, cnt, chiL, chiM, chiR, k, lc = L
                 _lib.check(lib.mpsb_apply_gate2(p2 + off * _lib.GATE2_DESC.itemsize, cnt, B, d, chiL, chiM, chiR,
                                                 k, lc, ws.data_ptr(), ws.numel(), pi + off * B * 8, st),
                            "mpsb_apply_gate2")
-        cp.n_launch_calls = len(cp.launches)
+                self._apps_since_rebalance += cnt
+            if self._apps_since_rebalance >= REBALANCE_EVERY_LAYERS * max(1, self.n // 2):
+                self.rebalance()
+                cp.n_rebalance_calls += 1
+        cp.n_launch_calls = len(cp.launches) + cp.n_rebalance_calls
         self.bonds = list(cp.bonds_out)
         if cp.staging is not None and cp.staging.cap == _RING_SLOT_BYTES:
             ev = _torch().cuda.Event()
@@ -397,6 +414,34 @@ class DeviceChain:
             self._status_flags.append(cp.info[: len(cp.plan.apps2) * B, 0].max())
             if len(self._status_flags) >= 256:
                 self._status_flags = [_torch().stack(self._status_flags).max()]
+
+    def rebalance(self, spread_log2: int = REBALANCE_SPREAD_LOG2) -> None:
+        """Even out the binary exponents of the sites of every chain (``mpsb_rebalance_sites``).
+
+        The reference's alternating left/right-canonical sweeps fix only the PRODUCT of the site
+        scales; in a long circuit the scale migrates between sites geometrically (complex128 has
+        the exponent range for it, complex64 reaches its limits after ~240 brickwork layers).
+        ``run()`` calls this every ``REBALANCE_EVERY_LAYERS`` layers' worth of applications; it
+        moves nothing while the exponents are within ``spread_log2`` of each other, and what it
+        moves are powers of two that multiply to one, so every contraction of the chain is
+        unchanged bit for bit.  Works on the whole site slots (capacity, not live bonds), so it
+        is valid in the middle of a plan."""
+        lib = _lib.load(require_device=True)
+        torch = _torch()
+        self._apps_since_rebalance = 0
+        key = (self._layout_gen, self.slab.data_ptr())
+        if self._rebalance_bufs is None or self._rebalance_bufs[0] != key:
+            refs = np.zeros(self.n, dtype=_lib.SITE_REF)
+            for i in range(self.n):
+                refs[i] = (self.site_ptr(i), self.total, self.caps[i], self.caps[i + 1])
+            shifts = torch.empty(self.n * self.B, dtype=torch.int32, device=self.device)
+            max_elems = max(self.caps[i] * self.d * self.caps[i + 1] for i in range(self.n))
+            self._rebalance_bufs = (key, _lib.to_device_bytes(refs, self.device), shifts, max_elems)
+        _, refs_dev, shifts, max_elems = self._rebalance_bufs
+        with torch.cuda.device(self.device):
+            _lib.check(lib.mpsb_rebalance_sites(refs_dev.data_ptr(), self.n, self.B, self.d, int(spread_log2),
+                                                shifts.data_ptr(), max_elems, _lib.stream_ptr(self.device)),
+                       "mpsb_rebalance_sites")
 
     def check_status(self) -> int:
         """Largest SVD status word of every run() since the last call (0 = all converged); warns

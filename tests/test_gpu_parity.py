@@ -535,3 +535,63 @@ def test_non_unitary_gate_orthonormalizes_and_renormalizes():      # core_test.p
     assert max(ora.bond_dimensions()) < 16                    # the projectors did reduce the middle bonds
     assert abs(m.norm() - ora.norm()) < 1e-4
     assert fidelity(m.wavefunction(), ora.wavefunction()) >= 1 - FID_TOL
+
+
+# ---- site-scale drift of long circuits (complex64 storage) -----------------------------------------
+def test_rebalance_is_exact_and_zero_sum():
+    """``mpsb_rebalance_sites``: power-of-two shifts that sum to zero per chain -- every site ends up
+    at about the same exponent and the wavefunction is unchanged bit for bit; a chain whose sites
+    are within the spread is not touched at all."""
+    import torch
+    import mpsim_b200 as mp
+    from mpsim_b200 import circuits
+    n = 10
+    mps = mp.MPS(n)
+    ops = circuits.brickwork(n, 6, seed=11)
+    mps._execute([(o.tensor, o.indices, {"keep_left_canonical": o.keep_left_canonical}) for o in ops])
+    chain = mps._chain
+    before = chain.slab.clone()
+    chain.rebalance()                                   # sites within 2**32 of each other: untouched
+    assert torch.equal(chain.slab, before)
+    wf0 = mps.wavefunction()
+    shifts = [40, -35, 0, 17, -22, 0, 0, 30, -30, 0]    # sums to zero: the state is the same
+    for i, sh in enumerate(shifts):
+        chain.set_site(i, chain.site_view(i).clone() * float(2.0 ** sh))
+    np.testing.assert_array_equal(mps.wavefunction(), wf0)
+    chain.rebalance()
+    ex = [int(np.floor(np.log2(float(chain.site_view(i).abs().max())))) for i in range(n)]
+    assert max(ex[:-1]) - min(ex[:-1]) <= 2, ex          # the last site takes the remainder of the sum
+    assert abs(ex[-1] - ex[0]) <= n + 2, ex
+    np.testing.assert_array_equal(mps.wavefunction(), wf0)
+    assert mps.norm() == pytest.approx(1.0, abs=1e-5)
+
+
+def test_long_untruncated_circuit_stays_in_range():
+    """320 brickwork layers on 12 qubits, nothing truncated.  The reference's alternating
+    left/right-canonical sweeps (core.py:1348-1360) let the scale of individual sites drift
+    geometrically -- the complex128 oracle ends this circuit with one site at 1e-49 and two at
+    1e24, beyond complex64 -- and run() rebalances the exponents on the way (powers of two whose
+    product is one).  The state must stay finite, normalised and equal to the oracle's."""
+    import mpsim_b200 as mp
+    from mpsim_b200 import circuits
+    n, depth = 12, 320
+    ops = circuits.brickwork(n, depth, seed=5)
+    ora = OracleMPS(n, dtype=np.complex128)
+    for op in ops:
+        ora.apply_two_qudit_gate(op.tensor, *op.indices, keep_left_canonical=op.keep_left_canonical)
+    mx = [float(np.abs(s).max()) for s in ora.sites]
+    assert min(mx) < 1e-38 and max(mx) > 1e18            # the drift is the algorithm's, not ours
+    mps = mp.MPS(n)
+    mps._execute([(o.tensor, o.indices, {"keep_left_canonical": o.keep_left_canonical}) for o in ops])
+    assert (mps.last_status()[:, 0] == 0).all()
+    ours = [float(mps._chain.site_view(i).abs().max()) for i in range(n)]
+    assert all(np.isfinite(ours)) and min(ours) > 1e-12 and max(ours) < 1e12, ours
+    assert abs(mps.norm() - 1.0) < 2e-4
+    wf, wref = mps.wavefunction(), ora.wavefunction()
+    assert np.isfinite(wf).all()
+    assert fidelity(wf, wref) >= 1 - 1e-4
+    # gate by gate (transient one-application plans) takes the same precaution
+    seq = mp.MPS(n)
+    for op in ops:
+        seq.apply_two_qudit_gate(mp.Node(op.tensor), *op.indices, keep_left_canonical=op.keep_left_canonical)
+    assert fidelity(seq.wavefunction(), wref) >= 1 - 1e-4
