@@ -37,7 +37,7 @@ constexpr int ST = 512;          // threads per CTA
 constexpr int NW = ST / 32;      // warps: one 8-row group each at nv = 128
 constexpr int XCH = 32;          // staging chunk of X: columns in step 4, rows in step 5
 constexpr int XS_ELEMS = 128 * (XCH + 1);   // >= XCH * (128 + 4)
-constexpr float BIG2 = 1e-4f * 1e-4f;       // a sweep without a rotation above this is the last
+constexpr float BIG2 = 1e-3f * 1e-3f;       // a sweep without a rotation above this cosine is the last (see jacobi_sweeps)
 
 // Profiling build only (MPSB_NVCC_EXTRA=-DMPSB_PROFILE, scripts/prof_svd.py): phase boundaries of
 // CTA 0 (clock64), read back through mpsb_debug_phase_clocks.  The release library carries neither
@@ -57,7 +57,7 @@ struct SvdSmallParams {
     cf* left; int64_t left_stride; cf* right; int64_t right_stride;   // output mode B
     float* svals; int64_t svals_stride;
     int32_t* info;
-    int max_sweeps; float tol2; int do_qr; int use_ns;
+    int max_sweeps; float tol2; float big2; int do_qr; int use_ns;
 };
 
 // MUFU approximations without the denormal / range wrappers of rsqrtf() and __fdividef(): the
@@ -192,7 +192,7 @@ __device__ __forceinline__ float reduce4(const float (&g)[4], int lane) {
 // rotations ("lite" update) -- one reduction chain per round instead of four, 30 % fewer instructions,
 // 4 % faster per sweep, but two more sweeps on graded spectra.
 template <int NP, int A0, int A1, int A2, int A3, int B0, int B1, int B2, int B3>
-__device__ __forceinline__ int sub_round(PRow<NP> (&y)[8], float (&a)[8], float tol2, int lane, bool& big) {
+__device__ __forceinline__ int sub_round(PRow<NP> (&y)[8], float (&a)[8], float tol2, float big2, int lane, bool& big) {
     constexpr int PA[4] = {A0, A1, A2, A3}, PB[4] = {B0, B1, B2, B3};
     float gr[4], gi[4];
 #pragma unroll
@@ -208,7 +208,7 @@ __device__ __forceinline__ int sub_round(PRow<NP> (&y)[8], float (&a)[8], float 
     const float apq = ap * aq;
     float c = 1.f, sr = 0.f, si = 0.f, tg = 0.f;
     const bool dorot = (g2 > tol2 * apq) && (g2 > 1e-30f);
-    big = big || (dorot && g2 > BIG2 * apq);
+    big = big || (dorot && g2 > big2 * apq);
     if (dorot) rot_params(ap, aq, mgr, mgi, g2, c, sr, si, tg);
     const unsigned bal = __ballot_sync(0xffffffffu, dorot);
     const unsigned flags = (bal & 1u) | ((bal >> 7) & 2u) | ((bal >> 14) & 4u) | ((bal >> 21) & 8u);
@@ -443,9 +443,13 @@ __device__ __noinline__ void householder(cf* A, int LS, int nrows, int ncols, in
 // group g takes its two blocks of the next round from groups g-1 and g+1 only, so a warp syncs with
 // its two neighbours (edge (g, g+1) = barrier 1 + g, even warps right edge first, odd warps left edge
 // first).  (Polling per-block round counters in shared memory was tried and was 3x slower.)
-// A sweep in which no rotation exceeded cos 1e-4 is the last one.
+// A sweep in which no rotation exceeded cos 1e-3 is the last one: on the thetas of the chi = 64 workload a
+// sweep whose largest rotation was eps leaves cosines of ~10 eps^2 (8.6e-3 -> 7.4e-4 -> 3e-6, the fp32 floor),
+// so after such a sweep the rows are orthogonal to ~1e-5, i.e. sigma to 1e-10 and the kept subspace to 1e-5
+// of an angle.  (1e-4, the first version: one more sweep on 35 % of the solves for identical singular values
+// and backward error; 3e-3 fails the 1e-5 singular-value test on one fixture.)
 template <int NP>
-__device__ __noinline__ void jacobi_sweeps(cf* Ys, int LS, float* nrm, int nb, int max_sweeps, float tol2,
+__device__ __noinline__ void jacobi_sweeps(cf* Ys, int LS, float* nrm, int nb, int max_sweeps, float tol2, float big2,
                                            int& sweeps_out, int& status_out) {
     constexpr int W = 64 * NP;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -502,14 +506,14 @@ __device__ __noinline__ void jacobi_sweeps(cf* Ys, int LS, float* nrm, int nb, i
                 for (int i = 0; i < 4; ++i) { a[i] = nrm[4 * I + i]; a[4 + i] = nrm[4 * Jb + i]; }
                 int nrot = 0;
                 if (r == 0) {                                    // inside the two blocks
-                    nrot += sub_round<NP, 0, 2, 4, 6, 1, 3, 5, 7>(v, a, tol2, lane, big);
-                    nrot += sub_round<NP, 0, 1, 4, 5, 2, 3, 6, 7>(v, a, tol2, lane, big);
-                    nrot += sub_round<NP, 0, 1, 4, 5, 3, 2, 7, 6>(v, a, tol2, lane, big);
+                    nrot += sub_round<NP, 0, 2, 4, 6, 1, 3, 5, 7>(v, a, tol2, big2, lane, big);
+                    nrot += sub_round<NP, 0, 1, 4, 5, 2, 3, 6, 7>(v, a, tol2, big2, lane, big);
+                    nrot += sub_round<NP, 0, 1, 4, 5, 3, 2, 7, 6>(v, a, tol2, big2, lane, big);
                 }
-                nrot += sub_round<NP, 0, 1, 2, 3, 4, 5, 6, 7>(v, a, tol2, lane, big);
-                nrot += sub_round<NP, 0, 1, 2, 3, 5, 6, 7, 4>(v, a, tol2, lane, big);
-                nrot += sub_round<NP, 0, 1, 2, 3, 6, 7, 4, 5>(v, a, tol2, lane, big);
-                nrot += sub_round<NP, 0, 1, 2, 3, 7, 4, 5, 6>(v, a, tol2, lane, big);
+                nrot += sub_round<NP, 0, 1, 2, 3, 4, 5, 6, 7>(v, a, tol2, big2, lane, big);
+                nrot += sub_round<NP, 0, 1, 2, 3, 5, 6, 7, 4>(v, a, tol2, big2, lane, big);
+                nrot += sub_round<NP, 0, 1, 2, 3, 6, 7, 4, 5>(v, a, tol2, big2, lane, big);
+                nrot += sub_round<NP, 0, 1, 2, 3, 7, 4, 5, 6>(v, a, tol2, big2, lane, big);
                 if (nrot) {
 #pragma unroll
                     for (int i = 0; i < 4; ++i) {
@@ -675,8 +679,8 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
     const int nb = 2 * ((nact + 7) / 8);           // 4-row blocks (even count)
     int sweeps = 0, status = 0;
     if (nact >= 2) {
-        if (P.LC == 128) jacobi_sweeps<2>(Ys, LS, nrm, nb, P.max_sweeps, P.tol2, sweeps, status);
-        else jacobi_sweeps<1>(Ys, LS, nrm, nb, P.max_sweeps, P.tol2, sweeps, status);
+        if (P.LC == 128) jacobi_sweeps<2>(Ys, LS, nrm, nb, P.max_sweeps, P.tol2, P.big2, sweeps, status);
+        else jacobi_sweeps<1>(Ys, LS, nrm, nb, P.max_sweeps, P.tol2, P.big2, sweeps, status);
     }
     const int W = P.LC;                            // rows < 4 nb are planar from here on (the others are zero)
     const int nplanar = nact >= 2 ? 4 * nb : 0;
@@ -903,10 +907,12 @@ int launch_svd_small(const cf* X, int64_t x_job_stride, int njobs, int nv, int L
     P.info = info;
     P.max_sweeps = 30;
     P.tol2 = 3e-6f * 3e-6f;
+    P.big2 = BIG2;
     P.do_qr = 1;
     P.use_ns = 1;
     // debugging knobs (not part of the ABI)
     if (const char* e = mpsb_env("MPSB_SVD_MAX_SWEEPS")) P.max_sweeps = atoi(e);
+    if (const char* e = mpsb_env("MPSB_SVD_LAST_COS")) { float c = (float)atof(e); P.big2 = c * c; }
     if (const char* e = mpsb_env("MPSB_SVD_NO_QR")) P.do_qr = atoi(e) ? 0 : 1;
     if (const char* e = mpsb_env("MPSB_SVD_NO_NS")) P.use_ns = atoi(e) ? 0 : 1;
     MPSB_CUDA(cudaFuncSetAttribute(svd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lo.smem));
