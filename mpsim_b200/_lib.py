@@ -110,4 +110,10 @@ def to_device_bytes(arr: np.ndarray, device):
 def stream_ptr(device=None) -> int:
     """Raw handle of torch's current stream on ``device`` (default: the current device)."""
     import torch
-    return torch.cuda.current_stream(device).cuda_stream
+    if device is None:
+        index = torch.cuda.current_device()
+    else:
+        index = torch.device(device).index
+        if index is None:
+            index = torch.cuda.current_device()
+    return torch._C._cuda_getCurrentRawStream(index)

@@ -57,7 +57,7 @@ struct SvdSmallParams {
     cf* left; int64_t left_stride; cf* right; int64_t right_stride;   // output mode B
     float* svals; int64_t svals_stride;
     int32_t* info;
-    int max_sweeps; float tol2; float big2; int do_qr; int use_ns;
+    int max_sweeps; float tol2; float big2; int do_qr; int use_ns; int colsort;
 };
 
 // MUFU approximations without the denormal / range wrappers of rsqrtf() and __fdividef(): the
@@ -638,6 +638,7 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
     float* tau_arr = nrm + nvp;                    // [nvp]
     int* perm = (int*)(tau_arr + nvp);             // [nvp]
     float* scal = (float*)(perm + nvp);            // [NW]  (also the QR scalars: 8 used)
+    unsigned char* colinv = (unsigned char*)(scal + NW + 16);    // [128] column of X held by column c of Y
 
     PHASE_MARK(0);
     // ---- step 0: load X scaled by an exact power of two so that max|x| is in [1, 2) ----------
@@ -664,7 +665,56 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
         if (i < nv && c < L) { v = X[(size_t)i * L + c]; v.x *= scale_in; v.y *= scale_in; }
         Ys[e] = v;
     }
+    for (int c = tid; c < 128; c += ST) colinv[c] = (unsigned char)c;
     __syncthreads();
+    // Columns in order of descending norm before the QR (the cheap part of column pivoting: the rows
+    // of R then come out graded and Jacobi needs ~0.5 sweeps fewer on the thetas of a truncated
+    // circuit; a full pivoted QR gains no more, scripts/exp_sweeps_preconditioning.py).  Stable, so
+    // equal columns -- diagonal and tied inputs -- stay where they are.  Y keeps the permuted
+    // columns to the end; step 4 reads the columns of X in the same order.
+    if (P.colsort && L >= 2) {
+        float* cnp = reinterpret_cast<float*>(Xs);             // [nparts][L] partial squared column norms
+        float* cn = cnp + ST;                                  // [L]
+        unsigned char* crank = reinterpret_cast<unsigned char*>(cn + 128);
+        // thread (c, part) sums rows part, part + nparts, ... of column c  (L <= 128 < ST); the parts are
+        // added in a fixed order (run-to-run reproducible ranks)
+        const int nparts = ST / L;
+        {
+            const int c = tid % L, part = tid / L;
+            if (part < nparts) {
+                float s2 = 0.f;
+                for (int i = part; i < nv; i += nparts) s2 += cf_abs2(Ys[(size_t)i * LS + c]);
+                cnp[part * L + c] = s2;
+            }
+        }
+        __syncthreads();
+        if (tid < L) {
+            float s2 = 0.f;
+            for (int part = 0; part < nparts; ++part) s2 += cnp[part * L + tid];
+            cn[tid] = s2;
+        }
+        __syncthreads();
+        if (tid < L) {
+            const float mine = cn[tid];
+            int rank = 0;
+            for (int j = 0; j < L; ++j) { const float o = cn[j]; rank += (o > mine) || (o == mine && j < tid); }
+            crank[tid] = (unsigned char)rank;
+            colinv[rank] = (unsigned char)tid;
+        }
+        __syncthreads();
+        // permute the columns of Y in place, a row per warp pass (the whole row is in registers
+        // before any of it is written)
+        for (int i = warp; i < nv; i += NW) {
+            cf* yr = Ys + (size_t)i * LS;
+            cf v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int c = lane + 32 * u; v[u] = c < L ? yr[c] : cf_make(0.f, 0.f); }
+            __syncwarp();
+#pragma unroll
+            for (int u = 0; u < 4; ++u) { const int c = lane + 32 * u; if (c < L) yr[crank[c]] = v[u]; }
+        }
+        __syncthreads();
+    }
 
     PHASE_MARK(1);
     // ---- step 1: Householder QR, R only ------------------------------------------------------
@@ -755,7 +805,7 @@ __global__ void __launch_bounds__(ST, 1) svd_small_kernel(SvdSmallParams P) {
             for (int e = tid; e < 128 * XCH; e += ST) {
                 const int a_ = e / XCH, cc = e - a_ * XCH;
                 cf v = cf_make(0.f, 0.f);
-                if (a_ < nv && cc < cw) { v = X[(size_t)a_ * L + c0 + cc]; v.x *= scale_in; v.y *= scale_in; }
+                if (a_ < nv && cc < cw) { v = X[(size_t)a_ * L + colinv[c0 + cc]]; v.x *= scale_in; v.y *= scale_in; }
                 Xs[a_ * (XCH + 1) + cc] = v;
             }
             __syncthreads();
@@ -874,7 +924,7 @@ Layout make_layout(int nv, int L) {
     lo.nvp = (nv + 7) / 8 * 8;
     lo.LC = L <= 64 ? 64 : 128;  // row width of the planar sweep layout (lanes cover 2 or 4 columns)
     lo.LS = lo.LC + 4;           // rows 16-byte aligned; 4 consecutive rows x 4 columns hit 16 distinct 8-byte banks
-    lo.smem = ((size_t)lo.nvp * lo.LS + XS_ELEMS + 2 * (size_t)VB + lo.nvp) * 8 + (size_t)lo.nvp * 16 + NW * 4 + 64;
+    lo.smem = ((size_t)lo.nvp * lo.LS + XS_ELEMS + 2 * (size_t)VB + lo.nvp) * 8 + (size_t)lo.nvp * 16 + NW * 4 + 64 + 128;
     return lo;
 }
 
@@ -910,9 +960,11 @@ int launch_svd_small(const cf* X, int64_t x_job_stride, int njobs, int nv, int L
     P.big2 = BIG2;
     P.do_qr = 1;
     P.use_ns = 1;
+    P.colsort = 1;
     // debugging knobs (not part of the ABI)
     if (const char* e = mpsb_env("MPSB_SVD_MAX_SWEEPS")) P.max_sweeps = atoi(e);
     if (const char* e = mpsb_env("MPSB_SVD_LAST_COS")) { float c = (float)atof(e); P.big2 = c * c; }
+    if (const char* e = mpsb_env("MPSB_SVD_NO_COLSORT")) P.colsort = atoi(e) ? 0 : 1;
     if (const char* e = mpsb_env("MPSB_SVD_NO_QR")) P.do_qr = atoi(e) ? 0 : 1;
     if (const char* e = mpsb_env("MPSB_SVD_NO_NS")) P.use_ns = atoi(e) ? 0 : 1;
     MPSB_CUDA(cudaFuncSetAttribute(svd_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)lo.smem));

@@ -42,7 +42,10 @@ def _on_device(fn):
 
     @functools.wraps(fn)
     def wrapper(self, *args, **kwargs):
-        with _torch().cuda.device(self.device):
+        torch = _torch()
+        if torch.cuda.current_device() == self.device.index:      # the usual case: no context switch
+            return fn(self, *args, **kwargs)
+        with torch.cuda.device(self.device):
             return fn(self, *args, **kwargs)
     return wrapper
 
@@ -144,10 +147,19 @@ class DeviceChain:
 
     @_on_device
     def ensure_caps(self, caps: Sequence[int]) -> None:
-        """Grow bond capacities (re-lays the slab out and copies the live tensors)."""
+        """Grow bond capacities (re-lays the slab out and copies the live tensors).  A single chain
+        grows a bond to at least twice its capacity (bounded by what the bond can ever reach,
+        d**min(i, n - i)), so that gate-by-gate use re-lays the slab out O(log chi) times instead of
+        at every application that widens a bond; batches are sized exactly (their slabs are GBs)."""
         new = [max(a, b) for a, b in zip(self.caps, caps)]
         if new == self.caps:
             return
+        if self.B == 1:
+            for i in range(1, self.n):
+                if new[i] > self.caps[i]:
+                    e = min(i, self.n - i)
+                    bound = self.d ** e if e < 24 else 1 << 62
+                    new[i] = min(max(new[i], 2 * self.caps[i]), max(bound, new[i]))
         old_slab, old_offs = self.slab, self.offs
         self._alloc(new)
         for i in range(self.n):
