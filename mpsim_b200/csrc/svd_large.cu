@@ -42,6 +42,7 @@ struct LargeParams {
     int* gcount;                 // [njobs][npairs]: arrival counter of the split Gram (zero between launches)
     cf* gpart;                   // [njobs][npairs][nsplit][P*P] partial Gram matrices (nsplit > 1 only)
     int nsplit;                  // CTAs sharing one pair's Gram (column ranges)
+    int gram_tc;                 // the Grams come from bj_gram_tc_kernel: gpart = [njobs][npairs][re | im][P*P] floats
     float* sigma; int* perm; int64_t s_stride;   // [nvp]
     Misc* misc;
     int nv, L, nvp, nb, npairs;
@@ -207,6 +208,17 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 1 : 3) bj_gram_evd_kernel(
         }
         cp_async_commit();
     };
+    if (p.gram_tc) {
+        // G was formed on the tensor cores (bj_gram_tc_kernel): the upper triangle of the two planes, mirrored
+        const float* gp = reinterpret_cast<const float*>(p.gpart) + ((size_t)job * p.npairs + g) * (2 * P * P);
+        for (int e = threadIdx.x; e < P * P; e += NTHR) {
+            const int r = e / P, c = e % P;
+            const int eu = r <= c ? e : c * P + r;
+            const float re = __ldcg(gp + eu), im = r == c ? 0.f : __ldcg(gp + P * P + eu);
+            Gs[r][c] = cf_make(re, r <= c ? im : -im);
+        }
+        __syncthreads();
+    } else {
     cf acc[4][4];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -320,6 +332,7 @@ __global__ void __launch_bounds__(NTHR, NTHR == 512 ? 1 : 3) bj_gram_evd_kernel(
         }
         __syncthreads();
     }
+    }   // !p.gram_tc
     // scale by a power of two so that max|G| is in [1, 2)   (every warp derives the same factor)
     float mx = 0.f;
     for (int i = 0; i < P; ++i) { cf v = Gs[i][lane]; mx = fmaxf(mx, fmaxf(fabsf(v.x), fabsf(v.y))); }
@@ -839,6 +852,221 @@ __global__ void __launch_bounds__(TA_THREADS, 1) bj_apply_tc_kernel(LargeParams 
     }
 }
 
+// ---- the pair Grams on the tensor cores ---------------------------------------------------------
+// G = Xp Xp^H of a block pair is a REAL product of the rows as they lie in memory: with r_i the
+// interleaved (re, im) row i (2L floats) and r~_i = (im, -re) of the same row,
+//   Re G_ij = r_i . r_j,      Im G_ij = r~_i . r_j        (G_ij = sum_c x_ic conj(x_jc)).
+// The contraction index is the contiguous one, so both operands are K-major as they come.  One MMA
+// tile carries TWO pairs:  A = [r(1) | r(2) | r~(1) | r~(2)]  (4 x 32 rows = M 128),  B = rows 0..63
+// of the same tile (N = 64), D = A B^T:  Re G(1) = D[0:32, 0:32], Re G(2) = D[32:64, 32:64],
+// Im G(1) = D[64:96, 0:32], Im G(2) = D[96:128, 32:64] (the cross-pair blocks are computed and
+// dropped: the tensor pipe has the time).  3xTF32: hi.lo + lo.hi + hi.hi per k-step, fp32
+// accumulation in TMEM over the whole row length.  The Gram only steers the rotation angles -- the
+// cyclic pass and the apply keep the state unitary -- so the per-MMA truncation of the accumulator
+// (diagonal entries come out ~1e-5 low at L = 2048) is harmless here; it is not chunked.
+// Loader warps read 32 complex columns of the 64 rows per stage (coalesced 16-byte loads), split and
+// write r and r~ straight into the K-major SWIZZLE_128B layout (row at r * 128 B per 32-float
+// k-block, 16-byte chunk j at j ^ (r & 7)): 16 KB read, 64 KB written, 24 MMAs per stage.
+// Persistent, one CTA per SM, items (job, two pairs) strided over the CTAs; the Grams go to global
+// memory as two planes of 32 x 32 floats per pair (p.gpart) for the pass (bj_gram_evd_kernel with
+// p.gram_tc set: no Gram of its own).
+// Used for rows of at least 1024 entries (chi >= 512).  Measured on B200 (profiles/r2_ab_tc_gram.txt): per
+// round, 4 x 2048^2: Gram + pass 120 us fused on FFMA -> 86 + 22 us (solve 766 -> 719 ms); 50 x 512^2:
+// 119 us -> 66 + 51 us, no gain, so the fused FFMA kernel keeps the shorter rows.  The kernel is bound by
+// shared-memory bandwidth, not by the tensor pipe: a 32 x 32 Gram has no operand reuse to speak of -- per
+// k-step of 8 floats and pair the three TF32 products read 3 x (64 + 32) rows x 32 B = 9.2 KB (9 k cycles
+// per 512-column pair at 128 B/clk) on top of the 4x write amplification of the hi/lo, r/r~ copies.
+constexpr int TG_KC = 32;                               // complex columns per stage (2 k-blocks of 32 floats)
+constexpr int TG_KB = 128 * 128;                        // bytes of one k-block of the 128-row operand
+constexpr int TG_OP_BYTES = 2 * TG_KB;                  // hi (or lo) of a stage
+constexpr int TG_STAGE_BYTES = 2 * TG_OP_BYTES;         // 64 KB
+constexpr int TG_STAGES = 3;
+constexpr int TG_SMEM = TG_STAGES * TG_STAGE_BYTES + 1024;
+constexpr int TG_N = 64;
+constexpr int TG_PF = 4;                               // chunks a loader thread has in flight
+
+struct TgItem { int job, g0, npair; bool skip; };
+__device__ __forceinline__ TgItem tg_item(const LargeParams& p, long long it, int ngroups) {
+    TgItem w;
+    w.job = (int)(it / ngroups);
+    const int grp = (int)(it - (long long)w.job * ngroups);
+    w.g0 = 2 * grp;
+    w.npair = min(2, p.npairs - w.g0);
+    w.skip = !p.misc[w.job].active;
+    return w;
+}
+
+__global__ void __launch_bounds__(TA_THREADS, 1) bj_gram_tc_kernel(LargeParams p, int round, int njobs) {
+    using namespace tcx;
+    extern __shared__ __align__(1024) uint8_t tg_smem[];
+    __shared__ __align__(8) uint64_t full_bar[TG_STAGES], empty_bar[TG_STAGES], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+    uint8_t* ring = (uint8_t*)(((uintptr_t)tg_smem + 1023) & ~(uintptr_t)1023);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    griddep_wait();
+    if (warp == TA_EPI_WARPS && lane == 0) {
+        for (int s = 0; s < TG_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], TA_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(2u * TG_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    const int ngroups = (p.npairs + 1) / 2;
+    const long long total = (long long)njobs * ngroups;
+    const int nchunk = (p.L + TG_KC - 1) / TG_KC;
+
+    if (warp > TA_EPI_WARPS) {
+        // ===== loaders =====
+        const int lt = threadIdx.x - (TA_EPI_WARPS + 1) * 32;
+        const int c4 = lt & 7, rsub = lt >> 3;              // 8 threads per row (4 complex each), 32 rows per pass
+        unsigned n = 0;                                     // (a missing second pair is stored as zeros)
+        for (long long it = blockIdx.x; it < total; it += gridDim.x) {
+            const TgItem w = tg_item(p, it, ngroups);
+            if (w.skip) continue;
+            const cf* X = p.X + (size_t)w.job * p.x_stride;
+            // global rows of this thread: tile rows rsub (pair 1) and 32 + rsub (pair 2)
+            const cf* rowp[2];
+#pragma unroll
+            for (int q = 0; q < 2; ++q) {
+                int I, J;
+                pair_blocks(p.nb, round, min(w.g0 + q, p.npairs - 1), I, J);
+                rowp[q] = X + (size_t)pair_row(I, J, rsub) * p.L;
+            }
+            // Register prefetch, TG_PF chunks deep: the loads of chunk ch + TG_PF are issued as soon as chunk ch
+            // has been split and stored, so a stage never waits for a full memory round trip (the first
+            // version loaded, stored and signalled one chunk at a time and was slower than the FFMA Gram).
+            float4 v[TG_PF][2][2];
+            auto fetch = [&](int ch, float4 (&dst)[2][2]) {
+                // float4 number c4 + 8 h of the row's 16 in this chunk: the 8 threads of a row read 128
+                // contiguous bytes per instruction
+#pragma unroll
+                for (int q = 0; q < 2; ++q)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int c0 = ch * TG_KC + 2 * (c4 + 8 * h);
+                        const bool ok = ch < nchunk && q < w.npair && c0 + 1 < p.L;
+                        dst[q][h] = ok ? __ldcg(reinterpret_cast<const float4*>(rowp[q] + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+            };
+#pragma unroll
+            for (int u = 0; u < TG_PF; ++u) fetch(u, v[u]);
+            for (int chb = 0; chb < nchunk; chb += TG_PF) {
+#pragma unroll
+                for (int u = 0; u < TG_PF; ++u) {
+                    const int ch = chb + u;
+                    if (ch < nchunk) {                       // (block-uniform)
+                        const int s = (int)(n % TG_STAGES);
+                        uint8_t* st = ring + (size_t)s * TG_STAGE_BYTES;
+                        mbar_wait(&empty_bar[s], ((n / TG_STAGES) & 1) ^ 1);
+#pragma unroll
+                        for (int q = 0; q < 2; ++q)
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                // floats 4 (c4 + 8 h) .. + 3 of the stage's 64: k-block h, 16-byte chunk c4
+                                const int kb = h, j = c4;
+                                const int r0 = 32 * q + rsub, r1 = 64 + r0;
+                                float4 hi, lo, thi, tlo;
+                                split_tf32(v[u][q][h].x, hi.x, lo.x); split_tf32(v[u][q][h].y, hi.y, lo.y);
+                                split_tf32(v[u][q][h].z, hi.z, lo.z); split_tf32(v[u][q][h].w, hi.w, lo.w);
+                                thi = make_float4(hi.y, -hi.x, hi.w, -hi.z);      // r~ = (im, -re)
+                                tlo = make_float4(lo.y, -lo.x, lo.w, -lo.z);
+                                const int o0 = kb * TG_KB + r0 * 128 + ((j ^ (r0 & 7)) << 4);
+                                const int o1 = kb * TG_KB + r1 * 128 + ((j ^ (r1 & 7)) << 4);
+                                *reinterpret_cast<float4*>(st + o0) = hi;
+                                *reinterpret_cast<float4*>(st + TG_OP_BYTES + o0) = lo;
+                                *reinterpret_cast<float4*>(st + o1) = thi;
+                                *reinterpret_cast<float4*>(st + TG_OP_BYTES + o1) = tlo;
+                            }
+                        fetch(ch + TG_PF, v[u]);
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        named_bar_sync(1, TA_LOAD_THREADS);
+                        if (lt == 0) mbar_arrive(&full_bar[s]);
+                        ++n;
+                    }
+                }
+            }
+        }
+    } else if (warp == TA_EPI_WARPS) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_tf32(128, TG_N);
+            unsigned n = 0;
+            int na = 0;
+            for (long long it = blockIdx.x; it < total; it += gridDim.x) {
+                if (tg_item(p, it, ngroups).skip) continue;
+                const int a = na & 1;
+                mbar_wait(&acc_empty[a], ((na >> 1) & 1) ^ 1);
+                const uint32_t tmem_d = tmem_base + (uint32_t)a * TG_N;
+                for (int ch = 0; ch < nchunk; ++ch, ++n) {
+                    const int s = (int)(n % TG_STAGES);
+                    mbar_wait(&full_bar[s], (uint32_t)(n / TG_STAGES) & 1);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(ring + (size_t)s * TG_STAGE_BYTES);
+#pragma unroll
+                    for (int kb = 0; kb < 2; ++kb) {
+                        const uint64_t hi = umma_desc_k128(sa + kb * TG_KB), lo = umma_desc_k128(sa + TG_OP_BYTES + kb * TG_KB);
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+                            tc_mma_tf32(tmem_d, hi + adv, lo + adv, idesc, (ch | kb | ks) != 0);
+                            tc_mma_tf32(tmem_d, lo + adv, hi + adv, idesc, 1);
+                            tc_mma_tf32(tmem_d, hi + adv, hi + adv, idesc, 1);
+                        }
+                    }
+                    tc_commit(&empty_bar[s]);
+                }
+                tc_commit(&acc_full[a]);
+                ++na;
+            }
+        }
+    } else {
+        // ===== epilogue: warp 0 Re G(1), warp 1 Re G(2), warp 2 Im G(1), warp 3 Im G(2) =====
+        int na = 0;
+        for (long long it = blockIdx.x; it < total; it += gridDim.x) {
+            const TgItem w = tg_item(p, it, ngroups);
+            if (w.skip) continue;
+            const int a = na & 1;
+            mbar_wait(&acc_full[a], (na >> 1) & 1);
+            tc_fence_after();
+            const int q = warp & 1, plane = warp >> 1;
+            const uint32_t trow = tmem_base + (uint32_t)a * TG_N + (uint32_t)(32 * q) + ((uint32_t)(warp * 32) << 16);
+            float d[32];
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                float v[16];
+                tc_ld16(trow + c * 16, v);
+                tc_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) d[c * 16 + i] = v[i];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
+            if (q < w.npair) {
+                float* out = reinterpret_cast<float*>(p.gpart) + (((size_t)w.job * p.npairs + w.g0 + q) * 2 + plane) * (P * P) + lane * P;
+#pragma unroll
+                for (int c = 0; c < 8; ++c)
+                    reinterpret_cast<float4*>(out)[c] = make_float4(d[4 * c], d[4 * c + 1], d[4 * c + 2], d[4 * c + 3]);
+            }
+            ++na;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * TG_N) : "memory");
+    }
+}
+
 // R <- 3/2 I - 1/2 R   (Newton-Schulz factor)
 __global__ void bj_ns_kernel(cf* R, int64_t stride, int n) {
     cf* r = R + (size_t)blockIdx.y * stride;
@@ -971,7 +1199,7 @@ struct LargeRun {
     LargeLayout lo;
     OutParams o;
     cf *Rbuf, *Z2, *M0;
-    int njobs, nv, L, nrounds, ntx, ntz, max_outer, skip, nt_cta, pdl, gram_stages, gram_threads, tc_apply;
+    int njobs, nv, L, nrounds, ntx, ntz, max_outer, skip, nt_cta, pdl, gram_stages, gram_threads, tc_apply, tc_gram;
     cudaStream_t st;
     PinSlot* pin;
     int sweeps_queued = 0;
@@ -1054,6 +1282,12 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
     // at least two tiles per SM, otherwise the FFMA kernel (a single 256 x 256 matrix is 32 tiles)
     r.tc_apply = (long long)njobs * lo.npairs * (r.ntx + r.ntz) >= 2 * 148;
     if (const char* e = mpsb_env("MPSB_LARGE_TC_APPLY")) r.tc_apply = atoi(e) != 0;       // A/B timing
+    // ... and so is the tensor-core Gram (bj_gram_tc_kernel; 16-byte row loads: even row length and stride)
+    r.tc_gram = r.tc_apply && L >= 1024 && L % 2 == 0 && x_job_stride % 2 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+    if (const char* e = mpsb_env("MPSB_LARGE_TC_GRAM"))                                          // A/B timing
+        r.tc_gram = atoi(e) != 0 && L % 2 == 0 && x_job_stride % 2 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+    p.gram_tc = r.tc_gram ? 1 : 0;
+    if (r.tc_gram) p.nsplit = 1;
     r.skip = 0; r.max_outer = MAX_OUTER;
     if (const char* e = mpsb_env("MPSB_LARGE_SKIP")) r.skip = atoi(e);
     if (const char* e = mpsb_env("MPSB_LARGE_SWEEPS")) r.max_outer = atoi(e);
@@ -1078,6 +1312,7 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
     if (!attrs) {
         MPSB_CUDA(cudaFuncSetAttribute(bj_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, APPLY_SMEM));
         MPSB_CUDA(cudaFuncSetAttribute(bj_apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
+        MPSB_CUDA(cudaFuncSetAttribute(bj_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
         MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes(GRAM_MAX_STAGES)));
         MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes(GRAM_MAX_STAGES)));
         MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes(GRAM_MAX_STAGES)));
@@ -1107,7 +1342,14 @@ static int large_enqueue_sweep(LargeRun& r) {
     // comparison covers (25 sweeps x 127 rounds).  Solves that run longer finish on the FFMA kernel.
     const bool tc_apply = r.tc_apply && (long long)r.sweeps_queued * r.nrounds < TC_APPLY_MAX_ROUNDS;
     for (int rd = 0; rd < r.nrounds; ++rd) {
-        if (!(r.skip & 1)) {
+        if (!(r.skip & 1) && r.tc_gram) {
+            const long long items = (long long)r.njobs * ((lo.npairs + 1) / 2);
+            cfg.gridDim = dim3((unsigned)(items < 148 ? items : 148));
+            cfg.blockDim = dim3(TA_THREADS); cfg.dynamicSmemBytes = TG_SMEM;
+            MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_gram_tc_kernel, p, rd, r.njobs));
+            cfg.gridDim = dim3(lo.npairs, r.njobs, 1); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = gram_smem_bytes(2);
+            MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_gram_evd_kernel<256, false>, p, rd, rd == 0 ? 1 : 0, 2));
+        } else if (!(r.skip & 1)) {
             cfg.gridDim = dim3(lo.npairs, r.njobs, p.nsplit); cfg.dynamicSmemBytes = gram_smem_bytes(r.gram_stages);
             if (r.gram_threads == 512) {
                 cfg.blockDim = dim3(512);
