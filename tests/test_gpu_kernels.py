@@ -249,3 +249,15 @@ def test_svd_large_both_apply_kernels(monkeypatch, shape, tc):
     (the library reads the switch at call time) and hold both to the LAPACK bounds above."""
     monkeypatch.setenv("MPSB_LARGE_TC_APPLY", str(tc))
     test_svd_large_matches_lapack(shape, 1)
+
+
+@pytest.mark.parametrize("tg", [0, 1])
+@pytest.mark.parametrize("shape", [(512, 512), (160, 128), (130, 300), (200, 136)])
+def test_svd_large_both_gram_kernels(monkeypatch, shape, tg):
+    """The pair Grams come from the fused FFMA kernel or, for rows of >= 1024 entries in full launches,
+    from bj_gram_tc_kernel (tcgen05 3xTF32, two pairs per MMA tile).  Force each in turn on shapes that
+    would not choose it: an odd number of pairs (160 rows: the second pair of the last tile is missing),
+    ragged row lengths (300, 136: partial chunks) and 512^2."""
+    monkeypatch.setenv("MPSB_LARGE_TC_GRAM", str(tg))
+    test_svd_large_matches_lapack(shape, 1)
+    test_svd_large_matches_lapack(shape, 0)
