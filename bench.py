@@ -30,9 +30,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 # dram bytes per 128 x 128 job of svd_small_kernel and where that number comes from (ncu --set full capture)
-SVD_SMALL_DRAM_BYTES_PER_JOB = (20.460e6 + 0.173e6) / 148.0
-SVD_SMALL_TRAFFIC_SOURCE = ("profiles/r2_svd_small_ncu_full.txt (ncu --set full of the kernel as of commit 3df04ef; 148 jobs: "
-                            "20.46 MB read + 0.17 MB written; algorithmic 128 KB in + 128 KB out per job)")
+SVD_SMALL_DRAM_BYTES_PER_JOB = (20.165e6 + 0.133e6) / 148.0
+SVD_SMALL_TRAFFIC_SOURCE = ("profiles/r2_svd_small_ncu_full.txt (ncu --set full of the kernel as of commit 71017ec; 148 jobs: "
+                            "20.16 MB read + 0.13 MB written; algorithmic 128 KB in + 128 KB out per job)")
 
 METRIC = "two_qudit_gate_applications_per_sec"
 UNIT = "applications/s"
