@@ -62,11 +62,12 @@ class _Staging:
     and pinned a fresh gate buffer and made two blocking pageable uploads per compile, which serialised
     host and device on every ``apply_two_qudit_gate`` call."""
 
-    def __init__(self, nbytes: int, device: Any) -> None:
+    def __init__(self, nbytes: int, device: Any, host=None, dev=None) -> None:
         torch = _torch()
         self.cap = int(nbytes)
-        self.host = torch.zeros(self.cap, dtype=torch.uint8).pin_memory()
-        self.dev = torch.empty(self.cap, dtype=torch.uint8, device=device)
+        # (host, dev): views of a larger pair -- the slots of a chain's ring share ONE pinned allocation
+        self.host = torch.zeros(self.cap, dtype=torch.uint8).pin_memory() if host is None else host
+        self.dev = torch.empty(self.cap, dtype=torch.uint8, device=device) if dev is None else dev
         self.event = None            # recorded after the last run() that read this slot
 
     def wait(self) -> None:
@@ -74,6 +75,9 @@ class _Staging:
             self.event.synchronize()
             self.event = None
 
+
+#: bond capacity a single chain grows to at once (bounded by d**min(i, n - i)), see ensure_caps
+_SINGLE_CHAIN_MIN_CAP = 64
 
 #: small plans (gate-by-gate use of the API) draw their staging from a ring of reusable slots
 _RING_SLOTS = 32
@@ -155,11 +159,16 @@ class DeviceChain:
         if new == self.caps:
             return
         if self.B == 1:
+            # (every interior bond goes to at least _SINGLE_CHAIN_MIN_CAP on the first growth: a 20-qubit chain
+            # at capacity 64 is 1.3 MB, and the first layers of a circuit would otherwise re-lay the slab out
+            # -- n slice copies -- every time a gate widens a bond for the first time: 35 times in 95 calls)
             for i in range(1, self.n):
+                e = min(i, self.n - i)
+                bound = self.d ** e if e < 24 else 1 << 62
+                want = max(new[i], _SINGLE_CHAIN_MIN_CAP)
                 if new[i] > self.caps[i]:
-                    e = min(i, self.n - i)
-                    bound = self.d ** e if e < 24 else 1 << 62
-                    new[i] = min(max(new[i], 2 * self.caps[i]), max(bound, new[i]))
+                    want = max(want, 2 * self.caps[i])
+                new[i] = max(new[i], min(want, bound))
         old_slab, old_offs = self.slab, self.offs
         self._alloc(new)
         for i in range(self.n):
@@ -242,9 +251,12 @@ class DeviceChain:
         only when 32 later plans are already in flight), a buffer of its own for a large one."""
         if nbytes > _RING_SLOT_BYTES:
             return _Staging(nbytes, self.device)
-        if len(self._ring) < _RING_SLOTS:
-            self._ring.append(_Staging(_RING_SLOT_BYTES, self.device))
-            return self._ring[-1]
+        if not self._ring:
+            torch = _torch()
+            host = torch.zeros(_RING_SLOTS * _RING_SLOT_BYTES, dtype=torch.uint8).pin_memory()
+            dev = torch.empty(_RING_SLOTS * _RING_SLOT_BYTES, dtype=torch.uint8, device=self.device)
+            self._ring = [_Staging(_RING_SLOT_BYTES, self.device, host[i * _RING_SLOT_BYTES:(i + 1) * _RING_SLOT_BYTES],
+                                   dev[i * _RING_SLOT_BYTES:(i + 1) * _RING_SLOT_BYTES]) for i in range(_RING_SLOTS)]
         slot = self._ring[self._ring_next]
         self._ring_next = (self._ring_next + 1) % _RING_SLOTS
         slot.wait()
