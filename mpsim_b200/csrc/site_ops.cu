@@ -155,23 +155,30 @@ site_maxabs_kernel(const mpsb_site_ref* __restrict__ sites, int nbatch, int d, u
 __global__ void rebalance_shift_kernel(unsigned* __restrict__ maxbits, int nsites, int nbatch, int spread) {
     const int bi = blockIdx.x * blockDim.x + threadIdx.x;
     if (bi >= nbatch) return;
-    int lo = INT_MAX, hi = INT_MIN, cnt = 0, last = -1;
+    int lo = INT_MAX, hi = INT_MIN, cnt = 0;
     long long sum = 0;
     for (int s = 0; s < nsites; ++s) {
         unsigned b = maxbits[(size_t)s * nbatch + bi];
         if (!b) continue;
         int e = ilogbf(__uint_as_float(b));
-        lo = min(lo, e); hi = max(hi, e); sum += e; ++cnt; last = s;
+        lo = min(lo, e); hi = max(hi, e); sum += e; ++cnt;
     }
     const bool act = cnt > 1 && hi - lo > spread;
-    const int mean = act ? (int)floorf((float)sum / (float)cnt) : 0;
-    int given = 0;
+    // every site to exponent `mean`, the first `rem` of them to mean + 1: the shifts add up to
+    // cnt * mean + rem - sum = 0 exactly
+    long long mean = 0, rem = 0;
+    if (act) {
+        mean = sum / cnt;
+        if (sum - mean * cnt < 0) --mean;                   // floor division
+        rem = sum - mean * cnt;                             // 0 .. cnt - 1
+    }
+    int seen = 0;
     for (int s = 0; s < nsites; ++s) {
         unsigned b = maxbits[(size_t)s * nbatch + bi];
         int sh = 0;
         if (act && b) {
-            if (s == last) sh = -given;
-            else { sh = mean - ilogbf(__uint_as_float(b)); given += sh; }
+            sh = (int)mean - ilogbf(__uint_as_float(b)) + (seen < rem ? 1 : 0);
+            ++seen;
         }
         ((int*)maxbits)[(size_t)s * nbatch + bi] = sh;
     }

@@ -106,6 +106,7 @@ class CompiledPlan:
         self.bonds_out: List[int] = []
         self.n_launch_calls = 0
         self.n_rebalance_calls = 0
+        self.launch_bonds: List[Tuple[int, ...]] = []
 
 
 class DeviceChain:
@@ -317,6 +318,7 @@ class DeviceChain:
         p1 = p2 = 0
         ws_need = 0
         launches = []
+        launch_bonds: List[Tuple[int, ...]] = []      # bond dimensions once launch i (its whole layer) has run
         for layer in layers:
             if layer["one"]:
                 start = p1
@@ -361,6 +363,8 @@ class DeviceChain:
                 for idx in idxs:
                     a = plan.apps2[idx]
                     bonds[a.site + 1] = a.k
+            snapshot = tuple(bonds)
+            launch_bonds += [snapshot] * (len(launches) - len(launch_bonds))
         cp.desc1 = st.dev[:b1]
         cp.desc2 = st.dev[b1: b1 + b2]
         # group tables of the layer calls (host arrays; pointers into the uploaded descriptor table)
@@ -374,6 +378,7 @@ class DeviceChain:
             ws_need = max(ws_need, lib.mpsb_gate2_layer_workspace_bytes(tab.ctypes.data, len(tab), B, d))
             launches[li] = ("g2layer", tab)
         cp.launches = launches
+        cp.launch_bonds = launch_bonds
         cp.workspace_bytes = int(ws_need)
         cp.slab_ptr = self.slab.data_ptr()
         cp.layout_gen = self._layout_gen
@@ -409,7 +414,7 @@ class DeviceChain:
         d, B = self.d, self.B
         cp.n_rebalance_calls = 0
         p1, p2, pi = cp.desc1.data_ptr(), cp.desc2.data_ptr(), cp.info.data_ptr()
-        for L in cp.launches:
+        for li, L in enumerate(cp.launches):
             if L[0] == "g1":
                 _, off, cnt, max_elems = L
                 _lib.check(lib.mpsb_apply_gate1(p1 + off * _lib.GATE1_DESC.itemsize, cnt, B, d, max_elems, st),
@@ -426,7 +431,7 @@ class DeviceChain:
                            "mpsb_apply_gate2")
                 self._apps_since_rebalance += cnt
             if self._apps_since_rebalance >= REBALANCE_EVERY_LAYERS * max(1, self.n // 2):
-                self.rebalance()
+                self.rebalance(bonds=cp.launch_bonds[li])
                 cp.n_rebalance_calls += 1
         cp.n_launch_calls = len(cp.launches) + cp.n_rebalance_calls
         self.bonds = list(cp.bonds_out)
@@ -439,7 +444,7 @@ class DeviceChain:
             if len(self._status_flags) >= 256:
                 self._status_flags = [_torch().stack(self._status_flags).max()]
 
-    def rebalance(self, spread_log2: int = REBALANCE_SPREAD_LOG2) -> None:
+    def rebalance(self, spread_log2: int = REBALANCE_SPREAD_LOG2, bonds: Optional[Sequence[int]] = None) -> None:
         """Even out the binary exponents of the sites of every chain (``mpsb_rebalance_sites``).
 
         The reference's alternating left/right-canonical sweeps fix only the PRODUCT of the site
@@ -448,24 +453,23 @@ class DeviceChain:
         ``run()`` calls this every ``REBALANCE_EVERY_LAYERS`` layers' worth of applications; it
         moves nothing while the exponents are within ``spread_log2`` of each other, and what it
         moves are powers of two that multiply to one, so every contraction of the chain is
-        unchanged bit for bit.  Works on the whole site slots (capacity, not live bonds), so it
-        is valid in the middle of a plan."""
+        unchanged bit for bit.  ``bonds``: the bond dimensions at this point of a running plan
+        (default: the chain's current ones)."""
         lib = _lib.load(require_device=True)
         torch = _torch()
         self._apps_since_rebalance = 0
-        key = (self._layout_gen, self.slab.data_ptr())
-        if self._rebalance_bufs is None or self._rebalance_bufs[0] != key:
-            refs = np.zeros(self.n, dtype=_lib.SITE_REF)
-            for i in range(self.n):
-                refs[i] = (self.site_ptr(i), self.total, self.caps[i], self.caps[i + 1])
-            shifts = torch.empty(self.n * self.B, dtype=torch.int32, device=self.device)
-            max_elems = max(self.caps[i] * self.d * self.caps[i + 1] for i in range(self.n))
-            self._rebalance_bufs = (key, _lib.to_device_bytes(refs, self.device), shifts, max_elems)
-        _, refs_dev, shifts, max_elems = self._rebalance_bufs
+        bonds = list(self.bonds if bonds is None else bonds)
+        refs = np.zeros(self.n, dtype=_lib.SITE_REF)
+        for i in range(self.n):
+            refs[i] = (self.site_ptr(i), self.total, bonds[i], bonds[i + 1])
+        max_elems = max(bonds[i] * self.d * bonds[i + 1] for i in range(self.n))
+        if self._rebalance_bufs is None or self._rebalance_bufs.numel() < self.n * self.B:
+            self._rebalance_bufs = torch.empty(self.n * self.B, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
+            refs_dev = _lib.to_device_bytes(refs, self.device)
             _lib.check(lib.mpsb_rebalance_sites(refs_dev.data_ptr(), self.n, self.B, self.d, int(spread_log2),
-                                                shifts.data_ptr(), max_elems, _lib.stream_ptr(self.device)),
-                       "mpsb_rebalance_sites")
+                                                self._rebalance_bufs.data_ptr(), max(max_elems, 1),
+                                                _lib.stream_ptr(self.device)), "mpsb_rebalance_sites")
 
     def check_status(self) -> int:
         """Largest SVD status word of every run() since the last call (0 = all converged); warns
