@@ -871,11 +871,16 @@ __global__ void __launch_bounds__(TA_THREADS, 1) bj_apply_tc_kernel(LargeParams 
 // memory as two planes of 32 x 32 floats per pair (p.gpart) for the pass (bj_gram_evd_kernel with
 // p.gram_tc set: no Gram of its own).
 // Used for rows of at least 1024 entries (chi >= 512).  Measured on B200 (profiles/r2_ab_tc_gram.txt): per
-// round, 4 x 2048^2: Gram + pass 120 us fused on FFMA -> 86 + 22 us (solve 766 -> 719 ms); 50 x 512^2:
-// 119 us -> 66 + 51 us, no gain, so the fused FFMA kernel keeps the shorter rows.  The kernel is bound by
-// shared-memory bandwidth, not by the tensor pipe: a 32 x 32 Gram has no operand reuse to speak of -- per
-// k-step of 8 floats and pair the three TF32 products read 3 x (64 + 32) rows x 32 B = 9.2 KB (9 k cycles
-// per 512-column pair at 128 B/clk) on top of the 4x write amplification of the hi/lo, r/r~ copies.
+// round, 4 x 2048^2: Gram + pass 120 us fused on FFMA -> 80 + 22 us (solve 766 -> 708 ms, the chi = 1024 leg
+// of bench.py 7.7 -> 8.4 applications/s); 50 x 512^2: 119 us -> 64 + 51 us and the chi = 256 circuit
+// 908 -> 872 applications/s (a third launch per round), so the fused FFMA kernel keeps the shorter rows.
+// What bounds it (ncu, profiles/r2_gram_tc_ncu_full.txt: tensor pipe 36 %, DRAM 1.6 TB/s, loader warps on the
+// long scoreboard): fence.proxy.async is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, i.e. it waits for every load
+// the thread has in flight, so a loader cannot prefetch across its own fence; with one chunk of loads in
+// flight per loader group (registers) an SM has 48 KB outstanding.  The next step is raw row tiles by TMA
+// into a deeper ring with converter warps reading them from shared memory.  The MMAs themselves are
+// shared-memory heavy (per k-step and pair 3 x (64 + 32) rows x 32 B = 9.2 KB of operand reads: a 32 x 32
+// Gram has no reuse to speak of), which puts the floor near 35 us per round at 50 x 512^2.
 constexpr int TG_KC = 32;                               // complex columns per stage (2 k-blocks of 32 floats)
 constexpr int TG_KB = 128 * 128;                        // bytes of one k-block of the 128-row operand
 constexpr int TG_OP_BYTES = 2 * TG_KB;                  // hi (or lo) of a stage
@@ -883,7 +888,9 @@ constexpr int TG_STAGE_BYTES = 2 * TG_OP_BYTES;         // 64 KB
 constexpr int TG_STAGES = 3;
 constexpr int TG_SMEM = TG_STAGES * TG_STAGE_BYTES + 1024;
 constexpr int TG_N = 64;
-constexpr int TG_PF = 4;                               // chunks a loader thread has in flight
+constexpr int TG_GROUPS = TG_STAGES;                   // loader groups: group q owns stage q (chunks q, q + 3, ...)
+constexpr int TG_GT = 64;                               // threads per loader group
+constexpr int TG_THREADS = (TA_EPI_WARPS + 1) * 32 + TG_GROUPS * TG_GT;      // 352
 
 struct TgItem { int job, g0, npair; bool skip; };
 __device__ __forceinline__ TgItem tg_item(const LargeParams& p, long long it, int ngroups) {
@@ -896,7 +903,7 @@ __device__ __forceinline__ TgItem tg_item(const LargeParams& p, long long it, in
     return w;
 }
 
-__global__ void __launch_bounds__(TA_THREADS, 1) bj_gram_tc_kernel(LargeParams p, int round, int njobs) {
+__global__ void __launch_bounds__(TG_THREADS, 1) bj_gram_tc_kernel(LargeParams p, int round, int njobs) {
     using namespace tcx;
     extern __shared__ __align__(1024) uint8_t tg_smem[];
     __shared__ __align__(8) uint64_t full_bar[TG_STAGES], empty_bar[TG_STAGES], acc_full[2], acc_empty[2];
@@ -924,75 +931,99 @@ __global__ void __launch_bounds__(TA_THREADS, 1) bj_gram_tc_kernel(LargeParams p
     const int nchunk = (p.L + TG_KC - 1) / TG_KC;
 
     if (warp > TA_EPI_WARPS) {
-        // ===== loaders =====
+        // ===== loaders: TG_GROUPS groups of 64 threads; group q fills stage q, i.e. every TG_GROUPS-th chunk =====
+        // (as many groups as stages: a stage has ONE writer, so its empty/full phases advance in step with that
+        // group -- four groups on three stages let a group lap a slower one and overwrite a stage in use)
+        // fence.proxy.async compiles to MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC: it waits for every load the thread
+        // has in flight, so a thread cannot prefetch across its own fence (the first version of this kernel
+        // did, 4 chunks deep, and ran at the latency of one chunk at a time: 8 of 8 loader warps on the long
+        // scoreboard in ncu).  Here a group issues the loads of its NEXT chunk right after signalling the
+        // current one and the other groups' loads are in flight while it splits, stores and fences.
         const int lt = threadIdx.x - (TA_EPI_WARPS + 1) * 32;
-        const int c4 = lt & 7, rsub = lt >> 3;              // 8 threads per row (4 complex each), 32 rows per pass
-        unsigned n = 0;                                     // (a missing second pair is stored as zeros)
-        for (long long it = blockIdx.x; it < total; it += gridDim.x) {
-            const TgItem w = tg_item(p, it, ngroups);
-            if (w.skip) continue;
-            const cf* X = p.X + (size_t)w.job * p.x_stride;
-            // global rows of this thread: tile rows rsub (pair 1) and 32 + rsub (pair 2)
-            const cf* rowp[2];
-#pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                int I, J;
-                pair_blocks(p.nb, round, min(w.g0 + q, p.npairs - 1), I, J);
-                rowp[q] = X + (size_t)pair_row(I, J, rsub) * p.L;
+        const int grp = lt / TG_GT, gt = lt % TG_GT;
+        const int c4 = gt & 7, rsub = gt >> 3;              // 8 threads per row (2 x 16 bytes each), rows rsub + 8 rr
+        constexpr int RR = 32 / (TG_GT / 8);                // row slots per pair and thread (4)
+        float4 v[2][RR][2];
+        // chunk number n (counted over all items of this CTA) -> (item, chunk); group q owns n = q mod TG_GROUPS
+        long long it = blockIdx.x;
+        int ch = -1;                                        // position of the walk
+        unsigned n = 0;                                     // number of the chunk (it, ch) once ch >= 0
+        TgItem w = {};
+        bool have = false;
+        auto next_item = [&]() {                            // first non-skipped item at or after `it`
+            for (; it < total; it += gridDim.x) {
+                w = tg_item(p, it, ngroups);
+                if (!w.skip) return true;
             }
-            // Register prefetch, TG_PF chunks deep: the loads of chunk ch + TG_PF are issued as soon as chunk ch
-            // has been split and stored, so a stage never waits for a full memory round trip (the first
-            // version loaded, stored and signalled one chunk at a time and was slower than the FFMA Gram).
-            float4 v[TG_PF][2][2];
-            auto fetch = [&](int ch, float4 (&dst)[2][2]) {
-                // float4 number c4 + 8 h of the row's 16 in this chunk: the 8 threads of a row read 128
-                // contiguous bytes per instruction
+            return false;
+        };
+        // advance to this group's next chunk; returns false at the end
+        auto advance = [&](int steps) {
+            while (steps > 0) {
+                if (ch < 0) {
+                    if (!next_item()) return false;
+                    ch = 0;
+                    --steps;
+                    if (have) ++n; else have = true;
+                    continue;
+                }
+                const int room = nchunk - 1 - ch;
+                if (room >= steps) { ch += steps; n += steps; steps = 0; }
+                else { steps -= room; ch = -1; n += room; it += gridDim.x; }
+            }
+            return true;
+        };
+        auto fetch = [&]() {
+            int I0, J0, I1, J1;
+            pair_blocks(p.nb, round, min(w.g0, p.npairs - 1), I0, J0);
+            pair_blocks(p.nb, round, min(w.g0 + 1, p.npairs - 1), I1, J1);
+            const cf* X = p.X + (size_t)w.job * p.x_stride;
 #pragma unroll
-                for (int q = 0; q < 2; ++q)
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int rr = 0; rr < RR; ++rr) {
+                    const cf* row = X + (size_t)pair_row(q ? I1 : I0, q ? J1 : J0, rsub + 8 * rr) * p.L;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int c0 = ch * TG_KC + 2 * (c4 + 8 * h);
-                        const bool ok = ch < nchunk && q < w.npair && c0 + 1 < p.L;
-                        dst[q][h] = ok ? __ldcg(reinterpret_cast<const float4*>(rowp[q] + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-            };
-#pragma unroll
-            for (int u = 0; u < TG_PF; ++u) fetch(u, v[u]);
-            for (int chb = 0; chb < nchunk; chb += TG_PF) {
-#pragma unroll
-                for (int u = 0; u < TG_PF; ++u) {
-                    const int ch = chb + u;
-                    if (ch < nchunk) {                       // (block-uniform)
-                        const int s = (int)(n % TG_STAGES);
-                        uint8_t* st = ring + (size_t)s * TG_STAGE_BYTES;
-                        mbar_wait(&empty_bar[s], ((n / TG_STAGES) & 1) ^ 1);
-#pragma unroll
-                        for (int q = 0; q < 2; ++q)
-#pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                // floats 4 (c4 + 8 h) .. + 3 of the stage's 64: k-block h, 16-byte chunk c4
-                                const int kb = h, j = c4;
-                                const int r0 = 32 * q + rsub, r1 = 64 + r0;
-                                float4 hi, lo, thi, tlo;
-                                split_tf32(v[u][q][h].x, hi.x, lo.x); split_tf32(v[u][q][h].y, hi.y, lo.y);
-                                split_tf32(v[u][q][h].z, hi.z, lo.z); split_tf32(v[u][q][h].w, hi.w, lo.w);
-                                thi = make_float4(hi.y, -hi.x, hi.w, -hi.z);      // r~ = (im, -re)
-                                tlo = make_float4(lo.y, -lo.x, lo.w, -lo.z);
-                                const int o0 = kb * TG_KB + r0 * 128 + ((j ^ (r0 & 7)) << 4);
-                                const int o1 = kb * TG_KB + r1 * 128 + ((j ^ (r1 & 7)) << 4);
-                                *reinterpret_cast<float4*>(st + o0) = hi;
-                                *reinterpret_cast<float4*>(st + TG_OP_BYTES + o0) = lo;
-                                *reinterpret_cast<float4*>(st + o1) = thi;
-                                *reinterpret_cast<float4*>(st + TG_OP_BYTES + o1) = tlo;
-                            }
-                        fetch(ch + TG_PF, v[u]);
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        named_bar_sync(1, TA_LOAD_THREADS);
-                        if (lt == 0) mbar_arrive(&full_bar[s]);
-                        ++n;
+                        const bool ok = q < w.npair && c0 + 1 < p.L;
+                        v[q][rr][h] = ok ? __ldcg(reinterpret_cast<const float4*>(row + c0)) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
                 }
-            }
+        };
+        bool live = advance(grp + 1);                       // chunk number grp
+        if (live) fetch();
+        while (live) {
+            const int s = (int)(n % TG_STAGES);
+            uint8_t* st = ring + (size_t)s * TG_STAGE_BYTES;
+            mbar_wait(&empty_bar[s], ((n / TG_STAGES) & 1) ^ 1);
+#pragma unroll
+            for (int q = 0; q < 2; ++q)
+#pragma unroll
+                for (int rr = 0; rr < RR; ++rr)
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        // floats 4 (c4 + 8 h) .. + 3 of the stage's 64: k-block h, 16-byte chunk c4
+                        const int kb = h, j = c4;
+                        const int r0 = 32 * q + rsub + 8 * rr, r1 = 64 + r0;
+                        const float4 x = v[q][rr][h];
+                        float4 hi, lo, thi, tlo;
+                        split_tf32(x.x, hi.x, lo.x); split_tf32(x.y, hi.y, lo.y);
+                        split_tf32(x.z, hi.z, lo.z); split_tf32(x.w, hi.w, lo.w);
+                        thi = make_float4(hi.y, -hi.x, hi.w, -hi.z);      // r~ = (im, -re)
+                        tlo = make_float4(lo.y, -lo.x, lo.w, -lo.z);
+                        const int o0 = kb * TG_KB + r0 * 128 + ((j ^ (r0 & 7)) << 4);
+                        const int o1 = kb * TG_KB + r1 * 128 + ((j ^ (r1 & 7)) << 4);
+                        *reinterpret_cast<float4*>(st + o0) = hi;
+                        *reinterpret_cast<float4*>(st + TG_OP_BYTES + o0) = lo;
+                        *reinterpret_cast<float4*>(st + o1) = thi;
+                        *reinterpret_cast<float4*>(st + TG_OP_BYTES + o1) = tlo;
+                    }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            named_bar_sync(1 + grp, TG_GT);
+            if (gt == 0) mbar_arrive(&full_bar[s]);
+            live = advance(TG_GROUPS);
+            if (live) fetch();
         }
     } else if (warp == TA_EPI_WARPS) {
         // ===== MMA issuer =====
@@ -1345,7 +1376,7 @@ static int large_enqueue_sweep(LargeRun& r) {
         if (!(r.skip & 1) && r.tc_gram) {
             const long long items = (long long)r.njobs * ((lo.npairs + 1) / 2);
             cfg.gridDim = dim3((unsigned)(items < 148 ? items : 148));
-            cfg.blockDim = dim3(TA_THREADS); cfg.dynamicSmemBytes = TG_SMEM;
+            cfg.blockDim = dim3(TG_THREADS); cfg.dynamicSmemBytes = TG_SMEM;
             MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_gram_tc_kernel, p, rd, r.njobs));
             cfg.gridDim = dim3(lo.npairs, r.njobs, 1); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = gram_smem_bytes(2);
             MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_gram_evd_kernel<256, false>, p, rd, rd == 0 ? 1 : 0, 2));
