@@ -852,6 +852,250 @@ __global__ void __launch_bounds__(TA_THREADS, 1) bj_apply_tc_kernel(LargeParams 
     }
 }
 
+// ---- the tensor-core apply with TMA-fed raw tiles ------------------------------------------------
+// bj_apply_tc_kernel above is latency bound (ncu: 3.1 TB/s, tensor pipe 17 %, the loader warps on the long
+// scoreboard): its loaders hold one tile of global loads in registers, i.e. ~32 KB in flight per SM, and
+// the proxy fence after their shared-memory stores waits for whatever they have in flight, so they cannot
+// run ahead.  Here the rows come in by TMA -- two boxes of 16 rows x 128 complex columns per tile, blocks
+// I and J of the pair -- into a ring of four RAW 32 KB tiles (128 KB in flight per SM, no registers, no
+// thread waiting), and the converter warps read a raw tile from shared memory, split it and write the
+// swizzled K-major operands exactly as before.  Shared memory: two A stages (hi + lo, 64 KB each) so that the
+// conversion of tile n+1 overlaps the MMAs of tile n, ONE copy of B (the embedding of Q changes once per pair,
+// i.e. every ntx + ntz tiles: the converters then wait for the MMAs of the previous tile), two raw tiles.
+// (First version: one 96 KB operand stage and four raw tiles -- 119 -> 108 us per round at 50 x 512^2; the
+// kernel was then bound by the convert -> MMA -> convert chain of the single stage, not by the loads.)
+// Roles (448 threads): warps 0-3 epilogue, warp 4 MMA issuer, warp 5 TMA producer, warps 6-13 converters.
+constexpr int TB_RAW_BYTES = P * TA_M * (int)sizeof(cf);                 // 32 KB: 32 rows x 128 columns
+constexpr int TB_RAW_STAGES = 2;
+constexpr int TB_A_STAGE = 2 * TA_A_BYTES;                               // A_hi, A_lo of one tile: 64 KB
+constexpr int TB_OP_BYTES = 2 * TB_A_STAGE + 2 * TA_B_BYTES;             // two A stages + B_hi, B_lo: 160 KB
+constexpr int TB_SMEM = TB_OP_BYTES + TB_RAW_STAGES * TB_RAW_BYTES + 1024;
+constexpr int TB_CONV_WARPS = 8, TB_CONV_THREADS = TB_CONV_WARPS * 32;
+constexpr int TB_THREADS = (TA_EPI_WARPS + 2 + TB_CONV_WARPS) * 32;      // 448
+static_assert(TB_SMEM <= 232448, "shared memory of bj_apply_tma_kernel");
+
+__global__ void __launch_bounds__(TB_THREADS, 1)
+bj_apply_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_z,
+                    LargeParams p, int round, int ntx, int ntot, int njobs) {
+    using namespace tcx;
+    extern __shared__ __align__(1024) uint8_t tb_smem[];
+    __shared__ __align__(8) uint64_t raw_full[TB_RAW_STAGES], raw_empty[TB_RAW_STAGES], op_full[2], op_empty[2], acc_full[2], acc_empty[2];
+    __shared__ uint32_t tmem_slot;
+    uint8_t* op = (uint8_t*)(((uintptr_t)tb_smem + 1023) & ~(uintptr_t)1023);
+    uint8_t* raw = op + TB_OP_BYTES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    griddep_wait();
+    if (warp == TA_EPI_WARPS && lane == 0) {
+        for (int s = 0; s < TB_RAW_STAGES; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&op_full[a], 1); mbar_init(&op_empty[a], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&acc_full[a], 1); mbar_init(&acc_empty[a], TA_EPI_WARPS); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_slot)), "r"(2u * TA_N) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = tmem_slot;
+
+    const long long total = (long long)njobs * p.npairs * ntot;
+    const long long per = (total + gridDim.x - 1) / gridDim.x;
+    const long long it0 = per * blockIdx.x, it1 = min(total, it0 + per);
+
+    if (warp == TA_EPI_WARPS + 1) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            unsigned n = 0;
+            for (long long it = it0; it < it1; ++it) {
+                const TaItem w = ta_item(p, it, ntot);
+                if (w.skip) continue;
+                const int s = (int)(n % TB_RAW_STAGES);
+                mbar_wait(&raw_empty[s], ((n / TB_RAW_STAGES) & 1) ^ 1);
+                int I, J;
+                pair_blocks(p.nb, round, w.g, I, J);
+                const bool isx = w.tile < ntx;
+                const CUtensorMap* map = isx ? &map_x : &map_z;
+                const int c0f = 2 * TA_M * (isx ? w.tile : w.tile - ntx);         // first float of the tile's columns
+                uint8_t* dst = raw + (size_t)s * TB_RAW_BYTES;
+                mbar_expect_tx(&raw_full[s], TB_RAW_BYTES);
+                tma_load_3d(dst, map, &raw_full[s], c0f, I * BLK, w.job);
+                tma_load_3d(dst + TB_RAW_BYTES / 2, map, &raw_full[s], c0f, J * BLK, w.job);
+                ++n;
+            }
+        }
+    } else if (warp > TA_EPI_WARPS + 1) {
+        // ===== converters: raw tile -> registers (hi/lo split) -> swizzled K-major operands =====
+        const int lt = threadIdx.x - (TA_EPI_WARPS + 2) * 32, lw = lt >> 5;
+        long long held = -1;                               // pair whose B the operand stage holds
+        unsigned n = 0;
+        for (long long it = it0; it < it1; ++it) {
+            const TaItem w = ta_item(p, it, ntot);
+            if (w.skip) continue;
+            const int s = (int)(n % TB_RAW_STAGES);
+            const long long pr = (long long)w.job * p.npairs + w.g;
+            const bool newq = held != pr;
+            cf qv[P * P / TB_CONV_THREADS];
+            if (newq) {
+                const cf* Q = p.Q + (size_t)w.job * p.g_stride + (size_t)w.g * P * P;
+#pragma unroll
+                for (int j = 0; j < P * P / TB_CONV_THREADS; ++j) qv[j] = __ldcg(Q + lt + TB_CONV_THREADS * j);
+            }
+            constexpr int RPW = P / TB_CONV_WARPS, CPL = TA_M / 32;
+            cf v[RPW][CPL];
+            mbar_wait(&raw_full[s], (n / TB_RAW_STAGES) & 1);
+            const cf* rt = reinterpret_cast<const cf*>(raw + (size_t)s * TB_RAW_BYTES);
+#pragma unroll
+            for (int rr = 0; rr < RPW; ++rr)
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) v[rr][j] = rt[(lw * RPW + rr) * TA_M + lane + 32 * j];
+            const int s2 = (int)(n & 1);
+            uint8_t* as = op + (size_t)s2 * TB_A_STAGE;
+            mbar_wait(&op_empty[s2], ((n >> 1) & 1) ^ 1);   // the MMAs of tile n - 2 have read this A stage
+            if (newq && n > 0) mbar_wait(&op_empty[s2 ^ 1], ((n - 1) >> 1) & 1);    // ... and those of tile n - 1 the old B
+            // pair rows k, k + 1 of one column are adjacent in the operand row (8 bytes each): one 16-byte store
+            // per pair, and the 8 lanes of a swizzle period cover 128 contiguous bytes (conflict free; the 8-byte
+            // stores of bj_apply_tc_kernel are 2-way conflicted: 46 % of its shared-memory wavefronts in ncu)
+#pragma unroll
+            for (int rp = 0; rp < RPW / 2; ++rp) {
+                const int k = lw * RPW + 2 * rp;
+#pragma unroll
+                for (int j = 0; j < CPL; ++j) {
+                    const int m = lane + 32 * j;
+                    float4 hi, lo;
+                    split_tf32(v[2 * rp][j].x, hi.x, lo.x);
+                    split_tf32(v[2 * rp][j].y, hi.y, lo.y);
+                    split_tf32(v[2 * rp + 1][j].x, hi.z, lo.z);
+                    split_tf32(v[2 * rp + 1][j].y, hi.w, lo.w);
+                    const int off = ta_offset(m, k, TA_KB_A);
+                    *reinterpret_cast<float4*>(as + off) = hi;
+                    *reinterpret_cast<float4*>(as + TA_A_BYTES + off) = lo;
+                }
+            }
+            if (newq) {
+                held = pr;
+                uint8_t* bh = op + 2 * TB_A_STAGE;
+                uint8_t* bl = bh + TA_B_BYTES;
+#pragma unroll
+                for (int j = 0; j < P * P / TB_CONV_THREADS; ++j) {
+                    const int e = lt + TB_CONV_THREADS * j, i = e >> 5, k = e & 31;
+                    float rh, rl, ih, il;
+                    split_tf32(qv[j].x, rh, rl);
+                    split_tf32(qv[j].y, ih, il);
+                    const int o0 = ta_offset(2 * i, k, TA_KB_B), o1 = ta_offset(2 * i + 1, k, TA_KB_B);
+                    ta_store(bh, o0, rh, -ih);
+                    ta_store(bl, o0, rl, -il);
+                    ta_store(bh, o1, ih, rh);
+                    ta_store(bl, o1, il, rl);
+                }
+            }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");      // generic-proxy stores -> UMMA reads
+            named_bar_sync(1, TB_CONV_THREADS);
+            if (lt == 0) { mbar_arrive(&op_full[s2]); mbar_arrive(&raw_empty[s]); }
+            ++n;
+        }
+    } else if (warp == TA_EPI_WARPS) {
+        // ===== MMA issuer =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = idesc_tf32(TA_M, TA_N);
+            const uint32_t sa = smem_u32(op);
+            unsigned n = 0;
+            for (long long it = it0; it < it1; ++it) {
+                if (ta_item(p, it, ntot).skip) continue;
+                const int a = n & 1;
+                mbar_wait(&acc_empty[a], ((n >> 1) & 1) ^ 1);
+                mbar_wait(&op_full[a], (n >> 1) & 1);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + (uint32_t)a * TA_N;
+                const uint32_t sA = sa + (uint32_t)a * TB_A_STAGE, sB = sa + 2 * TB_A_STAGE;
+#pragma unroll
+                for (int kb = 0; kb < 2; ++kb) {
+                    const uint64_t ahi = umma_desc_k128(sA + kb * TA_KB_A), alo = umma_desc_k128(sA + TA_A_BYTES + kb * TA_KB_A);
+                    const uint64_t bhi = umma_desc_k128(sB + kb * TA_KB_B);
+                    const uint64_t blo = umma_desc_k128(sB + TA_B_BYTES + kb * TA_KB_B);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks) {
+                        const uint64_t adv = (uint64_t)((ks * 32) >> 4);
+                        tc_mma_tf32(tmem_d, ahi + adv, blo + adv, idesc, (kb | ks) != 0);
+                        tc_mma_tf32(tmem_d, alo + adv, bhi + adv, idesc, 1);
+                        tc_mma_tf32(tmem_d, ahi + adv, bhi + adv, idesc, 1);
+                    }
+                }
+                tc_commit(&op_empty[a]);
+                tc_commit(&acc_full[a]);
+                ++n;
+            }
+        }
+    } else {
+        // ===== epilogue: TMEM lane m = column c0 + m of the tile =====
+        unsigned n = 0;
+        for (long long it = it0; it < it1; ++it) {
+            const TaItem w = ta_item(p, it, ntot);
+            if (w.skip) continue;
+            const int a = n & 1;
+            mbar_wait(&acc_full[a], (n >> 1) & 1);
+            tc_fence_after();
+            const uint32_t trow = tmem_base + (uint32_t)a * TA_N + ((uint32_t)(warp * 32) << 16);
+            float d[TA_N];
+#pragma unroll
+            for (int c = 0; c < TA_N / 16; ++c) {
+                float v[16];
+                tc_ld16(trow + c * 16, v);
+                tc_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 16; ++i) d[c * 16 + i] = v[i];
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&acc_empty[a]);
+            int I, J;
+            pair_blocks(p.nb, round, w.g, I, J);
+            cf* base; int ld, c0, ncol;
+            if (w.tile < ntx) { base = p.X + (size_t)w.job * p.x_stride; ld = p.L; c0 = w.tile * TA_M; ncol = p.L; }
+            else { base = p.Z + (size_t)w.job * p.z_stride; ld = p.nvp; c0 = (w.tile - ntx) * TA_M; ncol = p.nvp; }
+            const int col = c0 + warp * 32 + lane;
+            if (col < ncol) {
+#pragma unroll
+                for (int i = 0; i < P; ++i)
+                    base[(size_t)pair_row(I, J, i) * ld + col] = cf_make(d[2 * i], d[2 * i + 1]);
+            }
+            ++n;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * TA_N) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFnL)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+// complex64 rows as fp32: tensor [njobs][rows][2 ncols] with the given strides (in complex numbers), box
+// [1][16 rows][256 floats], no swizzle (raw tiles)
+static int make_row_map(CUtensorMap* map, cf* base, int njobs, int rows, int ncols, int64_t row_stride, int64_t job_stride) {
+    static EncodeTiledFnL enc = nullptr;
+    if (!enc) {
+        void* fp = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fp, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            enc = (EncodeTiledFnL)fp;
+    }
+    if (!enc) return 1;
+    cuuint64_t dims[3] = {(cuuint64_t)(2 * ncols), (cuuint64_t)rows, (cuuint64_t)njobs};
+    cuuint64_t strides[2] = {(cuuint64_t)row_stride * 8, (cuuint64_t)job_stride * 8};
+    cuuint32_t box[3] = {(cuuint32_t)(2 * TA_M), (cuuint32_t)BLK, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : 2;
+}
+
 // ---- the pair Grams on the tensor cores ---------------------------------------------------------
 // G = Xp Xp^H of a block pair is a REAL product of the rows as they lie in memory: with r_i the
 // interleaved (re, im) row i (2L floats) and r~_i = (im, -re) of the same row,
@@ -1230,7 +1474,8 @@ struct LargeRun {
     LargeLayout lo;
     OutParams o;
     cf *Rbuf, *Z2, *M0;
-    int njobs, nv, L, nrounds, ntx, ntz, max_outer, skip, nt_cta, pdl, gram_stages, gram_threads, tc_apply, tc_gram;
+    int njobs, nv, L, nrounds, ntx, ntz, max_outer, skip, nt_cta, pdl, gram_stages, gram_threads, tc_apply, tc_gram, tma_apply;
+    CUtensorMap map_x, map_z;                // rows of X and Z for bj_apply_tma_kernel
     cudaStream_t st;
     PinSlot* pin;
     int sweeps_queued = 0;
@@ -1313,6 +1558,15 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
     // at least two tiles per SM, otherwise the FFMA kernel (a single 256 x 256 matrix is 32 tiles)
     r.tc_apply = (long long)njobs * lo.npairs * (r.ntx + r.ntz) >= 2 * 148;
     if (const char* e = mpsb_env("MPSB_LARGE_TC_APPLY")) r.tc_apply = atoi(e) != 0;       // A/B timing
+    // the TMA-fed variant of the tensor-core apply needs 16-byte aligned rows (bj_apply_tma_kernel)
+    r.tma_apply = 0;
+    if (r.tc_apply && L % 2 == 0 && x_job_stride % 2 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(p.Z) & 15) == 0) {
+        if (make_row_map(&r.map_x, X, njobs, lo.nvp, L, L, x_job_stride) == 0 &&
+            make_row_map(&r.map_z, p.Z, njobs, lo.nvp, lo.nvp, lo.nvp, (int64_t)lo.z) == 0)
+            r.tma_apply = 1;
+    }
+    if (const char* e = mpsb_env("MPSB_LARGE_TMA_APPLY")) r.tma_apply = r.tma_apply && atoi(e) != 0;   // A/B timing
     // ... and so is the tensor-core Gram (bj_gram_tc_kernel; 16-byte row loads: even row length and stride)
     r.tc_gram = r.tc_apply && L >= 1024 && L % 2 == 0 && x_job_stride % 2 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
     if (const char* e = mpsb_env("MPSB_LARGE_TC_GRAM"))                                          // A/B timing
@@ -1344,6 +1598,7 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
         MPSB_CUDA(cudaFuncSetAttribute(bj_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, APPLY_SMEM));
         MPSB_CUDA(cudaFuncSetAttribute(bj_apply_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TA_SMEM));
         MPSB_CUDA(cudaFuncSetAttribute(bj_gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM));
+        MPSB_CUDA(cudaFuncSetAttribute(bj_apply_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TB_SMEM));
         MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel<256, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes(GRAM_MAX_STAGES)));
         MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel<256, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes(GRAM_MAX_STAGES)));
         MPSB_CUDA(cudaFuncSetAttribute(bj_gram_evd_kernel<512, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, gram_smem_bytes(GRAM_MAX_STAGES)));
@@ -1393,7 +1648,12 @@ static int large_enqueue_sweep(LargeRun& r) {
                 MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_gram_evd_kernel<256, false>, p, rd, rd == 0 ? 1 : 0, r.gram_stages));
             }
         }
-        if (!(r.skip & 4) && tc_apply) {
+        if (!(r.skip & 4) && tc_apply && r.tma_apply) {
+            const long long items = (long long)r.njobs * lo.npairs * (r.ntx + r.ntz);
+            cfg.gridDim = dim3((unsigned)(items < 148 ? items : 148));
+            cfg.blockDim = dim3(TB_THREADS); cfg.dynamicSmemBytes = TB_SMEM;
+            MPSB_CUDA(cudaLaunchKernelEx(&cfg, bj_apply_tma_kernel, r.map_x, r.map_z, p, rd, r.ntx, r.ntx + r.ntz, r.njobs));
+        } else if (!(r.skip & 4) && tc_apply) {
             const long long items = (long long)r.njobs * lo.npairs * (r.ntx + r.ntz);
             cfg.gridDim = dim3((unsigned)(items < 148 ? items : 148));
             cfg.blockDim = dim3(TA_THREADS); cfg.dynamicSmemBytes = TA_SMEM;
