@@ -241,14 +241,18 @@ def test_svd_large_matches_lapack(shape, lc):
         assert abs(np.linalg.norm(left[j] @ right[j]) - np.linalg.norm(best)) < 1e-5 * np.linalg.norm(best)
 
 
-@pytest.mark.parametrize("tc", [0, 1])
+@pytest.mark.parametrize("tc", [0, 1, 2])
 @pytest.mark.parametrize("shape", [(512, 512), (200, 136), (130, 300)])
-def test_svd_large_both_apply_kernels(monkeypatch, shape, tc):
-    """The block rotation is applied by bj_apply_kernel (FFMA) or bj_apply_tc_kernel (tcgen05 3xTF32)
-    depending on the launch size; two matrices would always take the first.  Force each in turn
-    (the library reads the switch at call time) and hold both to the LAPACK bounds above."""
-    monkeypatch.setenv("MPSB_LARGE_TC_APPLY", str(tc))
+def test_svd_large_all_apply_kernels(monkeypatch, shape, tc):
+    """The block rotation is applied by bj_apply_kernel (FFMA, tc = 0), by bj_apply_tma_kernel (tcgen05
+    3xTF32 fed by TMA, tc = 1: the default of full launches) or by bj_apply_tc_kernel (the same MMAs fed
+    by loader warps, tc = 2: rows that are not 16-byte aligned); two matrices would always take the
+    first.  Force each in turn (the library reads the switches at call time) and hold all three to the
+    LAPACK bounds above, in both orientations (ragged row lengths 136 / 300 / 130 / 200)."""
+    monkeypatch.setenv("MPSB_LARGE_TC_APPLY", "0" if tc == 0 else "1")
+    monkeypatch.setenv("MPSB_LARGE_TMA_APPLY", "1" if tc == 1 else "0")
     test_svd_large_matches_lapack(shape, 1)
+    test_svd_large_matches_lapack(shape, 0)
 
 
 @pytest.mark.parametrize("tg", [0, 1])
