@@ -640,6 +640,20 @@ __device__ __forceinline__ TaItem ta_item(const LargeParams& p, long long it, in
     return w;
 }
 
+// the same with the two flag loads (global memory, ~1 us of latency on a role's serial path) done once per
+// (job, pair) instead of once per tile
+struct TaCursor { long long pr = -1; bool skip = false; };
+__device__ __forceinline__ TaItem ta_item_cached(const LargeParams& p, long long it, int ntot, TaCursor& c) {
+    TaItem w;
+    const long long pr = it / ntot;
+    w.tile = (int)(it - pr * ntot);
+    w.job = (int)(pr / p.npairs);
+    w.g = (int)(pr - (long long)w.job * p.npairs);
+    if (pr != c.pr) { c.pr = pr; c.skip = !p.misc[w.job].active || !p.rotflag[pr]; }
+    w.skip = c.skip;
+    return w;
+}
+
 // Operand stores of the loader warps.  The compiler emits generic ST.E.64 for them (the ring pointer
 // is derived from an aligned cast); building with -DTA_STS=1 (MPSB_NVCC_EXTRA, csrc/build.py) uses
 // explicit st.shared.v2.f32 instead -- a variant to A/B on hardware, not yet measured.
@@ -909,8 +923,9 @@ bj_apply_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         // ===== TMA producer =====
         if (lane == 0) {
             unsigned n = 0;
+            TaCursor cur;
             for (long long it = it0; it < it1; ++it) {
-                const TaItem w = ta_item(p, it, ntot);
+                const TaItem w = ta_item_cached(p, it, ntot, cur);
                 if (w.skip) continue;
                 const int s = (int)(n % TB_RAW_STAGES);
                 mbar_wait(&raw_empty[s], ((n / TB_RAW_STAGES) & 1) ^ 1);
@@ -931,8 +946,9 @@ bj_apply_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
         const int lt = threadIdx.x - (TA_EPI_WARPS + 2) * 32, lw = lt >> 5;
         long long held = -1;                               // pair whose B the operand stage holds
         unsigned n = 0;
+        TaCursor cur;
         for (long long it = it0; it < it1; ++it) {
-            const TaItem w = ta_item(p, it, ntot);
+            const TaItem w = ta_item_cached(p, it, ntot, cur);
             if (w.skip) continue;
             const int s = (int)(n % TB_RAW_STAGES);
             const long long pr = (long long)w.job * p.npairs + w.g;
@@ -1002,8 +1018,9 @@ bj_apply_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
             constexpr uint32_t idesc = idesc_tf32(TA_M, TA_N);
             const uint32_t sa = smem_u32(op);
             unsigned n = 0;
+            TaCursor cur;
             for (long long it = it0; it < it1; ++it) {
-                if (ta_item(p, it, ntot).skip) continue;
+                if (ta_item_cached(p, it, ntot, cur).skip) continue;
                 const int a = n & 1;
                 mbar_wait(&acc_empty[a], ((n >> 1) & 1) ^ 1);
                 mbar_wait(&op_full[a], (n >> 1) & 1);
@@ -1031,8 +1048,9 @@ bj_apply_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_cons
     } else {
         // ===== epilogue: TMEM lane m = column c0 + m of the tile =====
         unsigned n = 0;
+        TaCursor cur;
         for (long long it = it0; it < it1; ++it) {
-            const TaItem w = ta_item(p, it, ntot);
+            const TaItem w = ta_item_cached(p, it, ntot, cur);
             if (w.skip) continue;
             const int a = n & 1;
             mbar_wait(&acc_full[a], (n >> 1) & 1);
