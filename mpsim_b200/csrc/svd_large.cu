@@ -1578,8 +1578,9 @@ static int large_begin(LargeRun& r, cf* X, int64_t x_job_stride, int njobs, int 
     if (const char* e = mpsb_env("MPSB_LARGE_TC_APPLY")) r.tc_apply = atoi(e) != 0;       // A/B timing
     // the TMA-fed variant of the tensor-core apply needs 16-byte aligned rows (bj_apply_tma_kernel)
     r.tma_apply = 0;
-    if (r.tc_apply && L % 2 == 0 && x_job_stride % 2 == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
-        (reinterpret_cast<uintptr_t>(p.Z) & 15) == 0) {
+    // (and rows at least one box wide: shorter ones keep the loader-warp kernel)
+    if (r.tc_apply && L % 2 == 0 && L >= TA_M && lo.nvp >= TA_M && x_job_stride % 2 == 0 &&
+        (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(p.Z) & 15) == 0) {
         if (make_row_map(&r.map_x, X, njobs, lo.nvp, L, L, x_job_stride) == 0 &&
             make_row_map(&r.map_z, p.Z, njobs, lo.nvp, lo.nvp, lo.nvp, (int64_t)lo.z) == 0)
             r.tma_apply = 1;
