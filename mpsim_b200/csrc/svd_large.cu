@@ -10,8 +10,11 @@
 //     bj_apply    : Xp <- Q Xp,  Zp <- Q Zp            (P x P) . (P x (L + nv)), in place
 //   a job stops rotating (its launches become no-ops) after a sweep in which no pair rotated.
 // Replaces tn.split_node_full_svd -> np.linalg.svd for 2chi in {256, 512, 2048}
-// (mpsim/core.py:1132-1152).  The Gram step runs on FFMA tiles; the apply on tcgen05 3xTF32 for
-// full launches (bj_apply_tc_kernel) and on FFMA tiles for one- and two-matrix launches.
+// (mpsim/core.py:1132-1152).  The Gram step runs on FFMA tiles (bj_gram_evd_kernel) or, for rows of
+// >= 1024 entries in full launches, on tcgen05 3xTF32 (bj_gram_tc_kernel, then the pass alone); the
+// apply on tcgen05 3xTF32 for full launches -- rows by TMA into a raw ring and converter warps
+// (bj_apply_tma_kernel), loader warps where the rows are not 16-byte aligned (bj_apply_tc_kernel) --
+// and on FFMA tiles for one- and two-matrix launches (bj_apply_kernel).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 #include <vector>
