@@ -1142,8 +1142,9 @@ static int make_row_map(CUtensorMap* map, cf* base, int njobs, int rows, int nco
 // What bounds it (ncu, profiles/r2_gram_tc_ncu_full.txt: tensor pipe 36 %, DRAM 1.6 TB/s, loader warps on the
 // long scoreboard): fence.proxy.async is MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC, i.e. it waits for every load
 // the thread has in flight, so a loader cannot prefetch across its own fence; with one chunk of loads in
-// flight per loader group (registers) an SM has 48 KB outstanding.  The next step is raw row tiles by TMA
-// into a deeper ring with converter warps reading them from shared memory.  The MMAs themselves are
+// flight per loader group (registers) an SM has 48 KB outstanding.  Raw row tiles by TMA into a deeper ring with
+// converter warps (what bj_apply_tma_kernel does) were tried here too and bought nothing (66 / 83 us): with the
+// loads out of the way the kernel sits on its shared-memory traffic.  The MMAs themselves are
 // shared-memory heavy (per k-step and pair 3 x (64 + 32) rows x 32 B = 9.2 KB of operand reads: a 32 x 32
 // Gram has no reuse to speak of), which puts the floor near 35 us per round at 50 x 512^2.
 constexpr int TG_KC = 32;                               // complex columns per stage (2 k-blocks of 32 floats)
